@@ -1,0 +1,105 @@
+"""ctypes loader for hiergen's OpenMP helpers, with scipy fallbacks."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_hg_kernels.so")
+_SRC = os.path.join(_HERE, "csrc", "hg_kernels.cpp")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        subprocess.check_call(["g++", "-O3", "-march=x86-64-v2", "-fopenmp", "-shared", "-fPIC", "-o", _SO, _SRC])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            try:
+                build()
+            except Exception:
+                return None
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def _csr64(a):
+    a = a.tocsr()
+    return (np.ascontiguousarray(a.indptr, dtype=np.int64), np.ascontiguousarray(a.indices, dtype=np.int32),
+            np.ascontiguousarray(a.data, dtype=np.float64))
+
+
+def _mk(data, indices, indptr, shape):
+    ip = indptr.astype(np.int32) if indptr[-1] < 2**31 - 1 else indptr
+    m = sp.csr_matrix((data, indices, ip), shape=shape)
+    m.has_sorted_indices = True
+    return m
+
+
+def spgemm(a, b, use_native=True):
+    """C = A @ B with sorted column indices (explicit zeros kept)."""
+    L = lib() if use_native else None
+    if L is None:
+        c = (a @ b).tocsr()
+        c.sort_indices()
+        return c
+    ai, aj, av = _csr64(a)
+    bi, bj, bv = _csr64(b)
+    m = a.shape[0]
+    cnt = np.zeros(m, dtype=np.int64)
+    i64, i32, f64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_double
+    L.hg_spgemm_count(i64(m), _p(ai, i64), _p(aj, i32), _p(bi, i64), _p(bj, i32), _p(cnt, i64))
+    ci = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(cnt, out=ci[1:])
+    cj = np.empty(ci[-1], dtype=np.int32)
+    cv = np.empty(ci[-1], dtype=np.float64)
+    L.hg_spgemm_fill(i64(m), _p(ai, i64), _p(aj, i32), _p(av, f64), _p(bi, i64), _p(bj, i32), _p(bv, f64),
+                     _p(ci, i64), _p(cj, i32), _p(cv, f64))
+    return _mk(cv, cj, ci, (a.shape[0], b.shape[1]))
+
+
+def masked_powers(S, A, coeff, sparsity_order, use_native=True):
+    """acc = sum_{term>=s+2} coeff[term-1] * T_{term-1} on the sparsity of S = A^s."""
+    coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+    ncoef = coeff.size
+    L = lib() if use_native else None
+    if L is None:
+        mask = S.copy()
+        mask.data[:] = 1.0
+        T = S.copy()
+        acc = S.copy()
+        acc.data[:] = 0.0
+        for term in range(sparsity_order + 2, ncoef + 1):
+            T = (T @ A).multiply(mask).tocsr()
+            T = (T + 0.0 * mask).tocsr()  # restore full pattern (explicit zeros)
+            T.sort_indices()
+            acc = (acc + coeff[term - 1] * T + 0.0 * mask).tocsr()
+            acc.sort_indices()
+        return acc.data.copy() if acc.nnz == S.nnz else _align(acc, S)
+    si, sj, sv = _csr64(S)
+    ai, aj, av = _csr64(A)
+    out = np.zeros(S.nnz, dtype=np.float64)
+    i64, i32, f64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_double
+    L.hg_masked_powers(i64(S.shape[0]), _p(si, i64), _p(sj, i32), _p(sv, f64), _p(ai, i64), _p(aj, i32),
+                       _p(av, f64), ctypes.c_int(ncoef), ctypes.c_int(sparsity_order), _p(coeff, f64), _p(out, f64))
+    return out
+
+
+def _align(acc, S):
+    # values of acc at the pattern of S (acc pattern is a subset of S's)
+    out = np.zeros(S.nnz)
+    accd = acc.todok()
+    rows = np.repeat(np.arange(S.shape[0]), np.diff(S.indptr))
+    for t, (r, c) in enumerate(zip(rows, S.indices)):
+        out[t] = accd.get((r, c), 0.0)
+    return out
