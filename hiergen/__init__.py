@@ -12,6 +12,6 @@ reference's setup.  It is not bit-reproducible against a gfortran build
 on the measured path: it only produces the operators that both the CPU oracle
 and the CUDA path consume.
 """
-from .problems import adv_1d, adv_diff_fd, dg_upwind_surrogate, read_petsc_binary  # noqa: F401
+from .problems import adv_1d, adv_diff_fd, dg_upwind_surrogate, read_petsc_binary, parilu_factors  # noqa: F401
 from .setup import AirOptions, Hierarchy, Level, Inverse, build_hierarchy, build_pflareinv  # noqa: F401
 from .upload import feed  # noqa: F401

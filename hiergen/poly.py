@@ -94,7 +94,7 @@ def coefficients_power(A, poly_order, rng):
     for i in range(sub):
         K[:, i + 1] = A @ K[:, i]
     R = np.linalg.qr(K, mode="r")
-    g0 = np.zeros(sub + 1)
+    g0 = np.zeros(R.shape[0])   # fewer rows than columns on tiny levels (n == poly_order + 1)
     g0[0] = R[0, 0]
     return np.linalg.lstsq(R[:, 1:], g0, rcond=None)[0]
 

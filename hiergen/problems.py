@@ -189,3 +189,44 @@ def read_petsc_binary(path):
         else:
             raise ValueError("unknown PETSc class id %d at offset %d" % (cid, off))
     return mats, vecs
+
+
+def parilu_factors(A, tol=1e-4, max_sweeps=100):
+    """Matrix-form Chow ParILU(0) sweep of ``tests/ilu_factors.c:484-535`` followed by the left
+    scaling of U by 1/diag(U) (``:563-567``).  Returns (L, U_scaled, inv_diag_U_raw, sweeps).
+
+    L = unit lower factor on the strict-lower pattern of A (+ diagonal), U on the upper pattern.
+    Each sweep: M = L U; R_L = A_Lstrict - M|pat(Lstrict); R_U = A_U - M|pat(U); stop when
+    sqrt(|R_L|_F^2 + |R_U|_F^2) < tol*|A|_F; else L += R_L diag(U)^-1, U += R_U.
+    """
+    A = A.tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    rows = np.repeat(np.arange(n), np.diff(A.indptr))
+    lower = A.indices < rows
+    A_Ls = sp.csr_matrix((A.data[lower], (rows[lower], A.indices[lower])), shape=A.shape)
+    A_U = sp.csr_matrix((A.data[~lower], (rows[~lower], A.indices[~lower])), shape=A.shape)
+    mask_L = A_Ls.copy(); mask_L.data[:] = 1.0
+    mask_U = A_U.copy(); mask_U.data[:] = 1.0
+    L = (sp.identity(n, format="csr") + 0.0 * A_Ls).tocsr()
+    U = A_U.copy()
+    thr = tol * np.sqrt((A.data ** 2).sum())
+    sweeps = 0
+    for sweep in range(max_sweeps):
+        M = (L @ U).tocsr()
+        R_L = (A_Ls - M.multiply(mask_L)).tocsr()
+        R_U = (A_U - M.multiply(mask_U)).tocsr()
+        res = np.sqrt((R_L.data ** 2).sum() + (R_U.data ** 2).sum())
+        sweeps = sweep + 1
+        if res < thr:
+            break
+        inv_dU = 1.0 / U.diagonal()
+        L = (L + R_L @ sp.diags(inv_dU)).tocsr()
+        U = (U + R_U).tocsr()
+    inv_diag_U_raw = 1.0 / U.diagonal()
+    U = (sp.diags(inv_diag_U_raw) @ U).tocsr()
+
+    def fix(m):
+        m = m.tocsr(); m.sort_indices()
+        return sp.csr_matrix((m.data.astype(np.float64), m.indices.astype(np.int32), m.indptr.astype(np.int32)), shape=m.shape)
+    return fix(L), fix(U), inv_diag_U_raw, sweeps

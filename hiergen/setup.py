@@ -169,7 +169,13 @@ def make_inverse(A, inverse_type, poly_order, sparsity_order, matrix_free, diag_
         coeffs = np.stack((re, im), axis=1)
         if not matrix_free:
             raise NotImplementedError("assembled Newton-basis inverse is not restated; use matrix_free")
-        return Inverse("poly", inverse_type=inverse_type, coeffs=coeffs, diag_scale=diag_scale), None
+        asm = None
+        if want_assembled:
+            # STAND-IN: the reference assembles the Newton polynomial itself for the grid transfers
+            # (src/Gmres_Poly_Newton.F90:1094-1929); here the Arnoldi-basis polynomial of the same order
+            # is assembled instead.  Only Z / W (inputs of the apply) are affected.
+            asm = poly.assembled_poly_inverse(A, poly.coefficients_arnoldi(As, po, rng), po, so, diag_scale)
+        return Inverse("poly", inverse_type=inverse_type, coeffs=coeffs, diag_scale=diag_scale), asm
     if inverse_type in (poly.POWER, poly.ARNOLDI):
         As = A
         if diag_scale:

@@ -1,0 +1,56 @@
+"""Generate the committed fixtures of tests/golden/ (run in the build container, where
+/root/reference is mounted; the fixtures travel to the GPU box, the reference does not).
+
+  * <case>.npz          : a whole hierarchy (every operator the upload hook hands over), the seeded
+                          rhs and the oracle's PCApply output, for the cases in tests/cases.py:GOLDEN.
+  * ilu_mat_stream.npz  : BASELINE.json configs[4] -- L and U from the ParILU(0) sweep of
+                          /root/reference/tests/ilu_factors.c:484-567 on the reference's own fixture
+                          /root/reference/tests/data/mat_stream_2364 (PETSc binary), the Newton-basis
+                          roots of PCPFLAREINV (order 6, matrix-free, ilu_factors.c:122-126), rhs and
+                          the oracle's PCApply output.
+
+The reference holds no vector-level golden outputs for PCApply, so the stored
+outputs are the ORACLE's (pinned by the iteration-count bounds of tests/test_oracle_pins.py); they
+freeze the oracle against drift and give the GPU tests fixed inputs independent of hiergen's RNG.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import cases  # noqa: E402
+import hiergen  # noqa: E402
+import oracle  # noqa: E402
+from hiergen import io as hio, poly  # noqa: E402
+
+
+def main():
+    for name in cases.GOLDEN:
+        A, H = cases.build(name)
+        O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))
+        b = cases.rhs(A.shape[0])
+        x = O.apply(b)
+        hio.save(os.path.join(HERE, name + ".npz"), H, b=b, x_oracle=x)
+        print(name, A.shape[0], H.no_levels, os.path.getsize(os.path.join(HERE, name + ".npz")))
+    ref = "/root/reference/tests/data/mat_stream_2364"
+    mats, _ = hiergen.read_petsc_binary(ref)
+    L, U, idu, sweeps = hiergen.parilu_factors(mats[0])
+    out = {"sweeps": np.asarray(sweeps)}
+    b = cases.rhs(L.shape[0])
+    out["b"] = b
+    for nm, T in (("L", L), ("U", U)):
+        H = hiergen.build_pflareinv(T, poly.NEWTON, 6, 1, True)
+        O = hiergen.feed(H, oracle.OracleAIR(1))
+        out[nm + "_indptr"], out[nm + "_indices"], out[nm + "_data"] = T.indptr, T.indices, T.data
+        out[nm + "_roots"] = H.inv_coarse.coeffs
+        out[nm + "_y_oracle"] = O.inv_apply(1, oracle.INV_AFF, b)
+    np.savez_compressed(os.path.join(HERE, "ilu_mat_stream.npz"), **out)
+    print("ilu_mat_stream", L.shape[0], sweeps)
+
+
+if __name__ == "__main__":
+    main()

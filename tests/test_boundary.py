@@ -1,0 +1,140 @@
+"""CPU suite, part 2: the drop-in boundary.  The C-ABI library loads and exports every symbol that
+include/pflare_b200.h declares; the host mirror behaves like the reference's PC interface; without a
+GPU every compute entry point fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import hiergen
+import pflare_b200
+from pflare_b200 import _capi
+from hiergen import io as hio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "pflare_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pflare_b200_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_header_symbol(built_libs):
+    L = ctypes.CDLL(pflare_b200.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(L, s), "missing export %s" % s
+    # and the ctypes table covers exactly the header
+    assert sorted(_capi.SIGNATURES) == syms
+
+
+def test_no_oracle_or_cpu_path_in_product():
+    """The product package must never import/link the oracle (it is test infrastructure)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pflare_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "air_oracle" not in src, f
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu(built_libs):
+    with pytest.raises(pflare_b200.PflareB200Error) as e:
+        pflare_b200.DeviceAIR(2)
+    assert e.value.code == 10 and "no CPU fallback" in str(e.value)
+    A, H = cases.build("fd2d_25")
+    pc = pflare_b200.PC().setType("air").setHierarchy(H)
+    with pytest.raises(pflare_b200.PflareB200Error):
+        pc.apply(np.ones(A.shape[0]))
+
+
+def test_pc_mirror_error_behaviour():
+    pc = pflare_b200.PC()
+    with pytest.raises(ValueError):
+        pc.setType("gamg")                      # only 'air' and 'pflareinv' are registered (src/PCAIR.c:3649-3663)
+    with pytest.raises(RuntimeError):
+        pc.setUp()                              # PCSetUp before PCSetType
+    pc.setType("air")
+    with pytest.raises(RuntimeError):
+        pc.setUp()                              # no operators
+    assert pc.getType() == "air"
+
+
+class _Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def set_level(self, l, n, f, c, s):
+        self.calls.append(("level", l, n, len(f), len(c), tuple(s)))
+
+    def set_csr(self, l, which, m):
+        self.calls.append(("csr", l, which, m.shape, m.nnz))
+
+    def set_diag(self, l, which, d):
+        self.calls.append(("diag", l, which, len(d)))
+
+    def set_poly(self, l, which, t, c, ds):
+        self.calls.append(("poly", l, which, t, np.asarray(c).shape, bool(ds)))
+
+    def finalize(self):
+        self.calls.append(("finalize",))
+
+
+def test_upload_walk_hands_over_every_operator():
+    A, H = cases.build("fd2d_fcf")
+    r = pflare_b200.feed(H, _Recorder())
+    NL = H.no_levels
+    levels = [c for c in r.calls if c[0] == "level"]
+    assert [c[1] for c in levels] == list(range(1, NL + 1))
+    for l, lv in enumerate(H.levels, start=1):
+        which = sorted(c[2] for c in r.calls if c[0] in ("csr", "diag", "poly") and c[1] == l)
+        assert which == sorted([pflare_b200.AFF, pflare_b200.AFC, pflare_b200.ACF, pflare_b200.ACC,
+                                pflare_b200.INV_AFF, pflare_b200.INV_ACC, pflare_b200.R, pflare_b200.P])
+        assert levels[l - 1][2:5] == (lv.n, lv.is_fine.size, lv.is_coarse.size)
+    assert r.calls[-1] == ("finalize",)
+    assert sorted(c[2] for c in r.calls if c[0] != "level" and len(c) > 1 and c[1] == NL) == [pflare_b200.INV_AFF, pflare_b200.COARSE]
+
+
+def test_hierarchy_container_round_trip(tmp_path):
+    """Integer data (CF lists, CSR structure) must survive the container bit-exactly."""
+    A, H = cases.build("fd2d_ffcc_mf")
+    p = str(tmp_path / "h.npz")
+    hio.save(p, H)
+    H2, _ = hio.load(p)
+    assert H2.no_levels == H.no_levels
+    for a, b in zip(H.levels, H2.levels):
+        assert np.array_equal(a.is_fine, b.is_fine) and np.array_equal(a.is_coarse, b.is_coarse)
+        for nm in ("A_ff", "A_fc", "R", "P", "A_cf", "A_cc"):
+            ma, mb = getattr(a, nm), getattr(b, nm)
+            assert np.array_equal(ma.indptr, mb.indptr) and np.array_equal(ma.indices, mb.indices)
+            assert np.array_equal(ma.data, mb.data)
+        assert a.smooth_order == b.smooth_order
+        assert np.array_equal(a.inv_A_ff.coeffs, b.inv_A_ff.coeffs)
+
+
+def test_problem_generators_match_reference_stencils():
+    # tests/adv_1d.c:79-105
+    A = hiergen.adv_1d(5).toarray()
+    assert np.array_equal(A, np.eye(5) - np.eye(5, k=-1))
+    # tests/adv_diff_fd.c:434-491: interior row of the 2D upwind stencil, theta = pi/4, nondimensional
+    n = 8
+    A = hiergen.adv_diff_fd(n, n).tocsr()
+    i, j = 3, 4
+    row = A[j * n + i].toarray().ravel()
+    u = v = np.sqrt(0.5)
+    assert np.isclose(row[(j - 1) * n + i], -v) and np.isclose(row[j * n + i - 1], -u) and np.isclose(row[j * n + i], u + v)
+    assert A[0, 0] == 1.0 and A[0].nnz == 1                       # inflow row = identity
+    assert A.nnz == (n - 1) * (n - 1) * 3 + (2 * n - 1)

@@ -1,0 +1,191 @@
+"""GPU suite: parity of the CUDA path (through the C-ABI) against the CPU oracle on identical operators.
+
+Bar (BASELINE.json north_star): integer/index data bit-exact; fp64 V-cycle output relative L2
+difference <= 1e-12; outer GMRES iteration count equal (+-1) to the oracle's / within the reference's
+pinned bound.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import hiergen
+import oracle
+import pflare_b200
+from hiergen import io as hio, poly
+from krylov import gmres, richardson
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12          # north_star: relative L2 difference of the fp64 V-cycle output
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _oracle(H):
+    return hiergen.feed(H, oracle.OracleAIR(H.no_levels))
+
+
+def _device(H, **opts):
+    d = pflare_b200.DeviceAIR(H.no_levels)
+    for k, v in opts.items():
+        d.set_option(k, v)
+    hiergen.feed(H, d)
+    return d
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_vcycle_parity(built_libs, name):
+    A, H = cases.build(name)
+    b = cases.rhs(A.shape[0])
+    xo = _oracle(H).apply(b)
+    d = _device(H)
+    x = d.apply(b)
+    assert cases.rel_l2(x, xo) <= TOL, name
+    # repeated applies are deterministic and do not depend on leftover state
+    x2 = d.apply(b)
+    assert np.array_equal(x, x2)
+    d.close()
+
+
+@pytest.mark.parametrize("opts", [dict(graph=0), dict(tail_rows=0), dict(fuse=0), dict(tail_rows=100000, tail_nnz=1e9),
+                                  dict(graph=0, fuse=0, tail_rows=0)])
+@pytest.mark.parametrize("name", ["fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "fd2d_diagAff", "dg_mf", "fd2d_idealW"])
+def test_vcycle_parity_execution_modes(built_libs, name, opts):
+    A, H = cases.build(name)
+    b = cases.rhs(A.shape[0], seed=7)
+    xo = _oracle(H).apply(b)
+    d = _device(H, **opts)
+    assert cases.rel_l2(d.apply(b), xo) <= TOL
+    d.close()
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_golden_fixtures(built_libs, name):
+    H, g = hio.load(os.path.join(GOLD, name + ".npz"))
+    d = _device(H)
+    assert cases.rel_l2(d.apply(g["b"]), g["x_oracle"]) <= TOL
+    d.close()
+
+
+def test_golden_ilu_factors_pflareinv_newton(built_libs):
+    """configs[4]: PCPFLAREINV Newton-basis polynomial (matrix-free) on the ParILU factors of the reference's
+    own fixture tests/data/mat_stream_2364."""
+    import scipy.sparse as sp
+    z = np.load(os.path.join(GOLD, "ilu_mat_stream.npz"))
+    n = z["b"].size
+    for nm in ("L", "U"):
+        T = sp.csr_matrix((z[nm + "_data"], z[nm + "_indices"], z[nm + "_indptr"]), shape=(n, n))
+        H = hiergen.build_pflareinv(T, poly.NEWTON, 6, 1, True)
+        H.inv_coarse.coeffs = z[nm + "_roots"]
+        pc = pflare_b200.PC().setType("pflareinv").setHierarchy(H)
+        y = pc.apply(z["b"])
+        assert cases.rel_l2(y, z[nm + "_y_oracle"]) <= TOL
+        _, its, conv = richardson(T, z["b"], np.zeros(n), pc.apply, rtol=1e-6, max_it=100)
+        assert conv and its <= 5
+        pc.destroy()
+
+
+@pytest.mark.parametrize("name", sorted(cases.PFLAREINV_CASES))
+def test_pflareinv_parity(built_libs, name):
+    A, H = cases.build_inv(name)
+    x = cases.rhs(A.shape[0])
+    yo = _oracle(H).inv_apply(1, oracle.INV_AFF, x)
+    pc = pflare_b200.PC().setType("pflareinv").setHierarchy(H)
+    assert cases.rel_l2(pc.apply(x), yo) <= TOL
+    pc.destroy()
+
+
+@pytest.mark.parametrize("name", ["fd2d_64", "fd2d_fcf", "fd2d_cf", "fd2d_mf_neumann", "fd2d_ffcc_mf"])
+def test_level_smoother_and_inverse_parity(built_libs, name):
+    """Seams 2 and 3 of SURVEY.md section 8b: one mg_FC_point_richardson on a level, one inverse apply on a level."""
+    A, H = cases.build(name)
+    O = _oracle(H)
+    d = _device(H)
+    for l in (1, 2, H.no_levels - 1):
+        lv = H.levels[l - 1]
+        b, x0 = cases.rhs(lv.n, seed=l), cases.rhs(lv.n, seed=100 + l)
+        assert cases.rel_l2(d.fc_smooth(l, b, x0), O.fc_smooth(l, b, x0)) <= TOL
+        v = cases.rhs(lv.is_fine.size, seed=200 + l)
+        assert cases.rel_l2(d.inv_apply(l, pflare_b200.INV_AFF, v), O.inv_apply(l, oracle.INV_AFF, v)) <= TOL
+        if lv.inv_A_cc is not None:
+            v = cases.rhs(lv.is_coarse.size, seed=300 + l)
+            assert cases.rel_l2(d.inv_apply(l, pflare_b200.INV_ACC, v), O.inv_apply(l, oracle.INV_ACC, v)) <= TOL
+    d.close()
+
+
+def test_integer_data_round_trip_bit_exact(built_libs):
+    A, H = cases.build("fd2d_64")
+    d = _device(H)
+    for l, lv in enumerate(H.levels, start=1):
+        assert np.array_equal(d.get_is(l, 0), lv.is_fine)
+        assert np.array_equal(d.get_is(l, 1), lv.is_coarse)
+    d.close()
+
+
+@pytest.mark.parametrize("name,rtol,side,bound", [("adv1d_makefile", 1e-10, "right", 2), ("fd2d_25", 1e-5, "left", 5),
+                                                  ("fd3d_10_lump", 1e-10, "right", 4), ("fd2d_100_study", 1e-10, "right", 6)])
+def test_outer_gmres_iteration_counts(built_libs, name, rtol, side, bound):
+    A, H = cases.build(name)
+    n = A.shape[0]
+    pc = pflare_b200.PC().setType("air").setHierarchy(H)
+    _, its_gpu, conv = gmres(A, np.zeros(n), np.ones(n), pc.apply, rtol=rtol, side=side)
+    _, its_cpu, _ = gmres(A, np.zeros(n), np.ones(n), _oracle(H).apply, rtol=rtol, side=side)
+    assert conv and its_gpu <= bound and abs(its_gpu - its_cpu) <= 1
+    pc.destroy()
+
+
+def test_edge_cases(built_libs):
+    # zero rhs -> exactly zero; a single-level PCAIR is refused; wrong vector length is an error
+    A, H = cases.build("fd2d_25")
+    pc = pflare_b200.PC().setType("air").setHierarchy(H)
+    assert not np.any(pc.apply(np.zeros(A.shape[0])))
+    with pytest.raises(ValueError):
+        pc.apply(np.zeros(A.shape[0] + 1))
+    pc.destroy()
+    H1 = hiergen.build_pflareinv(A)
+    with pytest.raises(pflare_b200.PflareB200Error):
+        pflare_b200.PC().setType("air").setHierarchy(H1).setUp()
+    # two PCs alive at once (tests/ex6_two_airg.c: per-instance handles)
+    A2, H2 = cases.build("fd2d_64")
+    p1 = pflare_b200.PC().setType("air").setHierarchy(H)
+    p2 = pflare_b200.PC().setType("air").setHierarchy(H2)
+    b1, b2 = cases.rhs(A.shape[0]), cases.rhs(A2.shape[0])
+    x1, x2 = p1.apply(b1), p2.apply(b2)
+    assert cases.rel_l2(x1, _oracle(H).apply(b1)) <= TOL and cases.rel_l2(x2, _oracle(H2).apply(b2)) <= TOL
+    p1.destroy()
+    assert cases.rel_l2(p2.apply(b2), x2) == 0.0
+    p2.destroy()
+
+
+def test_rows_longer_than_a_tile(built_libs):
+    """A dense-ish coarse operator: rows longer than the kernel's nnz tile take the whole-CTA path."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    n = 3000
+    D = sp.random(n, n, density=0.002, random_state=5, format="lil")
+    D[7, :] = rng.random(n)            # one 3000-nnz row
+    D[11, :2500] = rng.random(2500)
+    A = (D.tocsr() + sp.identity(n) * 50.0).tocsr()
+    H = hiergen.build_pflareinv(A, poly.ARNOLDI, 4, 1, True)
+    x = cases.rhs(n)
+    yo = _oracle(H).inv_apply(1, oracle.INV_AFF, x)
+    pc = pflare_b200.PC().setType("pflareinv").setHierarchy(H)
+    assert cases.rel_l2(pc.apply(x), yo) <= TOL
+    pc.destroy()
+
+
+def test_medium_size_parity_and_linearity(built_libs):
+    """512^2 (262k rows, ~30 levels): parity against the oracle plus linearity of PCApply."""
+    A = hiergen.adv_diff_fd(512, 512)
+    H = hiergen.build_hierarchy(A, hiergen.AirOptions())
+    n = A.shape[0]
+    d = _device(H)
+    b1, b2 = cases.rhs(n, 1), cases.rhs(n, 2)
+    x1, x2 = d.apply(b1), d.apply(b2)
+    assert cases.rel_l2(x1, _oracle(H).apply(b1)) <= TOL
+    x12 = d.apply(2.5 * b1 - b2)
+    assert cases.rel_l2(x12, 2.5 * x1 - x2) <= 1e-11
+    st = d.stats()
+    assert st["kernel_launches"] > 0 and st["algorithmic_bytes"] > 12 * st["nnz_per_cycle"]
+    d.close()

@@ -1,0 +1,158 @@
+"""CPU suite, part 1: pin the oracle (oracle/air_oracle.c).
+
+The reference holds no vector-level golden outputs for PCApply; what its tests DO pin
+are iteration-count bounds (`-ksp_max_it N` in tests/Makefile, exit code 1 when not converged).  The
+oracle -- fed by hiergen, the restated setup -- must meet every one of those bounds for the configs
+BASELINE.json names; it is also cross-checked against an independent scipy evaluation of the cycle
+and frozen by the fixtures of tests/golden/.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import hiergen
+import oracle
+import pycycle
+from hiergen import io as hio, poly
+from krylov import gmres, richardson
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _oracle(H):
+    return hiergen.feed(H, oracle.OracleAIR(H.no_levels))
+
+
+def _its(A, M, rtol, side):
+    n = A.shape[0]
+    _, its, conv = gmres(A, np.zeros(n), np.ones(n), M, rtol=rtol, side=side)   # b = 0, x0 = 1 like the drivers
+    return its, conv
+
+
+# ------------------------------------------------------------------ the reference's known answers
+def test_pin_adv1d_makefile_537(built_libs):
+    A, H = cases.build("adv1d_makefile")
+    its, conv = _its(A, _oracle(H).apply, 1e-10, "right")
+    assert conv and its <= 2          # tests/Makefile:537-540 -ksp_max_it 2
+
+
+def test_pin_fd2d_run_check(built_libs):
+    A, H = cases.build("fd2d_25")
+    its, conv = _its(A, _oracle(H).apply, 1e-5, "left")
+    assert conv and its <= 5          # tests/Makefile:1322-1323 -ksp_max_it 5 (PETSc default rtol, left PC)
+
+
+def test_pin_fd3d_makefile_543(built_libs):
+    A, H = cases.build("fd3d_10_lump")
+    its, conv = _its(A, _oracle(H).apply, 1e-10, "right")
+    assert conv and its <= 4          # tests/Makefile:543-546 -ksp_max_it 4
+
+
+@pytest.mark.parametrize("n", [100, 200])
+def test_pin_fd2d_scaling_study(built_libs, n):
+    A = hiergen.adv_diff_fd(n, n)
+    H = hiergen.build_hierarchy(A, hiergen.AirOptions(a_lump=True, a_drop=1e-5, strong_threshold=0.99))
+    its, conv = _its(A, _oracle(H).apply, 1e-10, "right")
+    assert conv and its <= 6          # tests/Makefile:1128-1134 -ksp_max_it 6, grid independent
+
+
+@pytest.mark.parametrize("name", ["inv_newton_5_o16", "inv_newton_10_o50"])
+def test_pin_pflareinv_newton(built_libs, name):
+    A, H = cases.build_inv(name)
+    O = _oracle(H)
+    its, conv = _its(A, lambda v: O.inv_apply(1, oracle.INV_AFF, v), 1e-5, "left")
+    assert conv and its <= 1          # tests/Makefile:548-553 -ksp_max_it 1
+
+
+def test_pin_ilu_factors_newton(built_libs):
+    # configs[4]: Richardson + PCPFLAREINV Newton matrix-free on the ParILU factors, rtol 1e-6
+    # (tests/ilu_factors.c:122-126, run at tests/Makefile:105-109; the driver fails if not converged)
+    z = np.load(os.path.join(GOLD, "ilu_mat_stream.npz"))
+    import scipy.sparse as sp
+    n = z["b"].size
+    for nm in ("L", "U"):
+        T = sp.csr_matrix((z[nm + "_data"], z[nm + "_indices"], z[nm + "_indptr"]), shape=(n, n))
+        H = hiergen.build_pflareinv(T, poly.NEWTON, 6, 1, True)
+        H.inv_coarse.coeffs = z[nm + "_roots"]
+        O = _oracle(H)
+        y = O.inv_apply(1, oracle.INV_AFF, z["b"])
+        assert cases.rel_l2(y, z[nm + "_y_oracle"]) < 1e-13
+        _, its, conv = richardson(T, z["b"], np.zeros(n), lambda v: O.inv_apply(1, oracle.INV_AFF, v), rtol=1e-6, max_it=100)
+        assert conv and its <= 5
+
+
+# ------------------------------------------------------------------ oracle vs independent evaluation
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_oracle_matches_textbook_cycle(built_libs, name):
+    A, H = cases.build(name)
+    b = cases.rhs(A.shape[0])
+    x = _oracle(H).apply(b)
+    xr = pycycle.vcycle(H, b)
+    assert cases.rel_l2(x, xr) < 1e-9, name
+
+
+@pytest.mark.parametrize("name", sorted(cases.PFLAREINV_CASES))
+def test_oracle_inverse_matches_explicit_polynomial(built_libs, name):
+    A, H = cases.build_inv(name)
+    x = cases.rhs(A.shape[0])
+    y = _oracle(H).inv_apply(1, oracle.INV_AFF, x)
+    yr = pycycle.inv_apply(H.inv_coarse, H.coarse_matrix, x)
+    assert cases.rel_l2(y, yr) < 1e-8, name
+
+
+def test_horner_skips_zero_coefficients(built_libs):
+    # src/Gmres_Poly.F90:1468: a zero coefficient skips the matvec AND the shift (not Horner-exact)
+    A, H = cases.build_inv("inv_arnoldi_mf")
+    H.inv_coarse.coeffs = np.array([[1.0], [0.0], [0.5], [0.25]])
+    x = cases.rhs(A.shape[0])
+    y = _oracle(H).inv_apply(1, oracle.INV_AFF, x)
+    # reference order: y = c3 x; (order 2) y = A y + c2 x; (order 1 skipped); (order 0) y = A y + c0 x
+    t = 0.25 * x
+    t = A @ t + 0.5 * x
+    t = A @ t + 1.0 * x
+    assert cases.rel_l2(y, t) < 1e-14
+
+
+def test_newton_zero_roots_and_final_pair(built_libs):
+    A, H = cases.build_inv("inv_newton_noextra_mf")
+    # real zero root skipped, complex pair last => second matvec of the pair skipped (:845)
+    H.inv_coarse.coeffs = np.array([[2.0, 0.0], [0.0, 0.0], [1.5, 0.5], [1.5, -0.5]])
+    x = cases.rhs(A.shape[0])
+    y = _oracle(H).inv_apply(1, oracle.INV_AFF, x)
+    t = x.copy()
+    yy = t / 2.0
+    t = t - (A @ t) / 2.0
+    sq = 1.5 * 1.5 + 0.25
+    u = 3.0 * t - A @ t
+    yy = yy + u / sq
+    assert cases.rel_l2(y, yy) < 1e-14
+
+
+# ------------------------------------------------------------------ fixtures
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_golden_fixture_matches_oracle(built_libs, name):
+    H, d = hio.load(os.path.join(GOLD, name + ".npz"))
+    x = _oracle(H).apply(d["b"])
+    assert cases.rel_l2(x, d["x_oracle"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_golden_fixture_is_what_hiergen_builds(built_libs, name):
+    """The integer data of the fixture (CF lists) must be reproduced bit-exactly by the seeded generator."""
+    H, _ = hio.load(os.path.join(GOLD, name + ".npz"))
+    _, H2 = cases.build(name)
+    assert H.no_levels == H2.no_levels
+    for a, b in zip(H.levels, H2.levels):
+        assert np.array_equal(a.is_fine, b.is_fine) and np.array_equal(a.is_coarse, b.is_coarse)
+        assert np.array_equal(a.R.indices, b.R.indices) and np.array_equal(a.P.indices, b.P.indices)
+
+
+def test_cf_splitting_is_a_disjoint_cover(built_libs):
+    # structural assertion of tests/ex6_cf_splitting.c:34-64
+    A, H = cases.build("fd2d_64")
+    for lv in H.levels:
+        both = np.concatenate((lv.is_fine, lv.is_coarse))
+        assert both.size == lv.n and np.array_equal(np.sort(both), np.arange(lv.n))
+        assert np.all(np.diff(lv.is_fine) > 0) and np.all(np.diff(lv.is_coarse) > 0)
