@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- AIRG V-cycle apply (PCApply of PCAIR) on B200, BASELINE.json's metric.
+
+A "step" is ONE V-cycle: PCApply on one right-hand side, on the hierarchy of the workload
+(default: BASELINE.json configs[1], tests/adv_diff_fd.c 2D upwind advection 4096^2, default PCAIR
+options).  The hierarchy is an input (the reference's setup builds it; here hiergen restates that
+setup on the host before the timed region) and is uploaded once as device CSR.
+
+  value    : DOF/s = level-1 rows / V-cycle time, rhs and result resident in HBM, CUDA events on
+             the library's own stream, max over ranks.
+  e2e      : the same through the reference-facing call with HOST buffers (pinned): H2D of the rhs,
+             V-cycle, D2H of the result inside the timed region.
+  roofline : HBM; algorithmic bytes (SURVEY.md section 8d model, computed by the library per op) of the
+             spmv_stream_kernel launches / their summed CUDA-event durations.
+  cpu_baseline / --impl reference : the CPU oracle (OpenMP restatement of the reference's PETSc
+             path, kind "port": PETSc/gfortran are absent so the reference cannot be built) on the
+             same hierarchy, all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- workload
+def make_problem(args):
+    import hiergen
+    from hiergen import poly
+    w = args.workload
+    if w == "adv_diff_fd_2d":
+        n = args.n
+        A = hiergen.adv_diff_fd(n, n)
+        opts = hiergen.AirOptions()
+        name = "tests/adv_diff_fd.c 2D upwind advection %dx%d, default PCAIR (AIRG, assembled Arnoldi order 6, ff smoothing)" % (n, n)
+    elif w == "adv_diff_fd_2d_mf":
+        n = args.n
+        A = hiergen.adv_diff_fd(n, n)
+        opts = hiergen.AirOptions(matrix_free_polys=True)
+        name = "tests/adv_diff_fd.c 2D upwind advection %dx%d, PCAIR -pc_air_matrix_free_polys" % (n, n)
+    elif w == "adv_diff_fd_3d":
+        n = args.n
+        A = hiergen.adv_diff_fd(n, n, n)
+        opts = hiergen.AirOptions(a_lump=True)
+        name = "tests/adv_diff_fd.c 3D upwind advection %d^3, PCAIR -pc_air_a_lump" % n
+    elif w == "dg_upwind":
+        n = args.n
+        A = hiergen.dg_upwind_surrogate(n, n, 3)
+        opts = hiergen.AirOptions(matrix_free_polys=True)
+        name = "DG-P1 upwind surrogate %dx%d cells x3, PCAIR -pc_air_matrix_free_polys" % (n, n)
+    else:
+        raise SystemExit("unknown workload " + w)
+    return A, opts, name
+
+
+def build_hierarchy(args):
+    import hiergen
+    t = time.time()
+    A, opts, name = make_problem(args)
+    H = hiergen.build_hierarchy(A, opts, verbose=args.verbose)
+    log("[bench] hierarchy: %d rows, %d levels, built on the host in %.1f s" % (A.shape[0], H.no_levels, time.time() - t))
+    return A, H, name
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi style clock / throttle-reason sampling during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            log("[bench] NVML unavailable:", e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max), "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def time_oracle(H, n, cycles, warm=1):
+    import hiergen
+    import oracle
+    O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))
+    b = np.random.default_rng(1234).random(n)
+    for _ in range(warm):
+        O.apply(b)
+    ts = []
+    for _ in range(cycles):
+        t = time.perf_counter()
+        O.apply(b)
+        ts.append(time.perf_counter() - t)
+    return float(np.median(ts)), O.threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    A, H, name = build_hierarchy(args)
+    n = A.shape[0]
+    # each step = one V-cycle of the CPU path on the full workload (bounded: a cycle is O(1 s))
+    import hiergen
+    import oracle
+    O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))
+    b = np.random.default_rng(1234).random(n)
+    steps = max(1, min(args.steps, args.ref_max_steps))
+    for _ in range(min(args.warmup, 2)):
+        O.apply(b)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.apply(b)
+    dt = (time.perf_counter() - t0) / steps
+    val = n / dt
+    sample = "%d full V-cycles of the CPU oracle on the whole workload (%d rows)" % (steps, n)
+    out = {
+        "impl": "reference", "metric": "AIRG V-cycle DOF/s", "value": val, "unit": "DOF/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "rows": n, "levels": H.no_levels},
+        "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": O.threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import pflare_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- pflare_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    A, H, name = build_hierarchy(args)
+    n = A.shape[0]
+    if world > 1:
+        raise SystemExit("multi-GPU bench path not available yet")
+    pc = pflare_b200.PC(device=local).setType("air").setHierarchy(H)
+    t = time.time()
+    pc.setUp()
+    dev = pc.device()
+    log("[bench] upload + finalize: %.1f s" % (time.time() - t))
+    st = dev.stats()
+    stream = torch.cuda.ExternalStream(dev.stream_ptr(), device=torch.device("cuda", local))
+
+    b_host = torch.from_numpy(np.random.default_rng(1234).random(n)).pin_memory()
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    b = b_host.cuda()
+    x = torch.empty_like(b)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms / steps
+
+    # device-resident leg
+    with ClockSampler(local) as clk:
+        ms_dev = timed(lambda: dev.apply_ptr(b.data_ptr(), x.data_ptr(), 1), args.steps, args.warmup)
+    clocks = clk.summary()
+    # end-to-end leg: host (pinned) buffers through the reference-facing call
+    ms_e2e = timed(lambda: dev.apply_ptr(b_host.data_ptr(), x_host.data_ptr(), 0), args.steps, args.warmup)
+
+    # parity spot check on the fly (small cost): result is finite and deterministic
+    dev.synchronize()
+    xs = x.cpu().numpy()
+    assert np.all(np.isfinite(xs)) and np.array_equal(xs, x_host.numpy()), "device and host-buffer applies differ"
+
+    # roofline of the dominant kernel: per-launch CUDA events (graph off for this pass)
+    reps = 3
+    tot_ms = tot_by = 0.0
+    allms = allby = 0.0
+    biggest = (0.0, 0.0, 0)
+    for r in range(reps + 1):
+        ms, by, lev, kind = dev.profile_apply(b.data_ptr(), x.data_ptr())
+        if r == 0:
+            continue
+        is_spmv = kind != 6
+        tot_ms += float(ms[is_spmv].sum())
+        tot_by += float(by[is_spmv].sum())
+        allms += float(ms.sum())
+        allby += float(by.sum())
+        k = int(np.argmax(by))
+        biggest = (float(by[k]), float(ms[k]), int(lev[k]))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = tot_by / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+    roof = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "spmv_stream_kernel", "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650",
+        "how": "sum of algorithmic bytes of all spmv_stream_kernel launches of one V-cycle / sum of their CUDA-event durations (launch by launch, graph off)",
+        "cycle_achieved": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9,
+        "cycle_frac": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9 / peak,
+        "largest_launch": {"bytes": biggest[0], "ms": biggest[1], "level": biggest[2],
+                           "GBps": biggest[0] / (biggest[1] * 1e-3) / 1e9 if biggest[1] > 0 else None},
+        "algorithmic_bytes_per_cycle": st["algorithmic_bytes"], "nnz_per_cycle": st["nnz_per_cycle"],
+    }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t_cpu, threads = time_oracle(H, n, cycles=args.cpu_cycles)
+        cpu = {"value": n / t_cpu, "unit": "DOF/s", "cores": threads, "kind": "port",
+               "sample": "median of %d full V-cycles of the CPU oracle (OpenMP restatement of the PETSc path) on the whole workload" % args.cpu_cycles,
+               "ms_per_cycle": t_cpu * 1e3}
+
+    if rank == 0:
+        out = {
+            "metric": "AIRG V-cycle DOF/s", "value": n * world / (ms_dev * 1e-3) if False else n / (ms_dev * 1e-3),
+            "unit": "DOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "rows": n, "levels": H.no_levels, "nnz_level1": int(A.nnz),
+                       "l2": "inputs larger than L2: %.2f GB of operators streamed per cycle, no flush" % (st["algorithmic_bytes"] / 1e9),
+                       "device_bytes": st["device_bytes"], "rhs": "seeded uniform(0,1), seed 1234"},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "DOF/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
+            "gpu_launches": int(st["kernel_launches"]) * args.steps,
+            "launches_per_cycle": int(st["kernel_launches"]), "tail_levels": int(st["tail_levels"]),
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    pc.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PFLARE_BENCH_WORKLOAD", "adv_diff_fd_2d"))
+    ap.add_argument("--n", type=int, default=int(os.environ.get("PFLARE_BENCH_N", "4096")))
+    ap.add_argument("--cpu-cycles", type=int, default=5)
+    ap.add_argument("--ref-max-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
