@@ -63,12 +63,45 @@ def make_problem(args):
     return A, opts, name
 
 
+def cache_dir():
+    for d in (os.environ.get("PFLARE_BENCH_CACHE"), "/dev/shm", "/tmp"):
+        if d and os.path.isdir(d) and os.access(d, os.W_OK):
+            p = os.path.join(d, "pflare_b200_cache")
+            os.makedirs(p, exist_ok=True)
+            return p
+    return None
+
+
 def build_hierarchy(args):
+    """Build (or load from the per-box cache) the workload's hierarchy.  The cache only saves host
+    time between back-to-back bench invocations on one box (reference arm, b200 arm, N = 1/2/4/8);
+    it holds inputs, never results."""
     import hiergen
+    from hiergen import io as hio
     t = time.time()
     A, opts, name = make_problem(args)
+    cd = None if args.no_cache else cache_dir()
+    path = os.path.join(cd, "%s_%d.npz" % (args.workload, args.n)) if cd else None
+    if path and os.path.exists(path):
+        try:
+            H, _ = hio.load(path)
+            H.A = A
+            log("[bench] hierarchy: %d rows, %d levels, loaded from %s in %.1f s" % (A.shape[0], H.no_levels, path, time.time() - t))
+            return A, H, name
+        except Exception as e:
+            log("[bench] cache load failed (%s); rebuilding" % e)
     H = hiergen.build_hierarchy(A, opts, verbose=args.verbose)
     log("[bench] hierarchy: %d rows, %d levels, built on the host in %.1f s" % (A.shape[0], H.no_levels, time.time() - t))
+    if path and int(os.environ.get("RANK", "0")) == 0:
+        try:
+            t = time.time()
+            tmp = path + ".tmp.%d.npz" % os.getpid()
+            d = hio.to_dict(H, with_A=False)
+            np.savez(tmp, **d)
+            os.replace(tmp, path)
+            log("[bench] hierarchy cached at %s (%.1f s)" % (path, time.time() - t))
+        except Exception as e:
+            log("[bench] could not cache the hierarchy: %s" % e)
     return A, H, name
 
 
@@ -258,6 +291,17 @@ def run_gpu(args):
         allby += float(by.sum())
         k = int(np.argmax(by))
         biggest = (float(by[k]), float(ms[k]), int(lev[k]))
+        if r == reps and args.dump_ops and rank == 0:
+            tags = {1: "restrict Z", 2: "coarse", 3: "A_fc(+W)", 4: "A_ff resid", 5: "inverse", 6: "elementwise", 7: "fused local F", 8: "A_cf", 9: "A_cc"}
+            ltail = H.no_levels - int(st["tail_levels"]) + 1
+            nspmv = int(np.sum((kind != 6) & (lev < ltail) & (by > 0)))
+            with open(args.dump_ops + ".nspmv", "w") as f:
+                f.write("%d\n" % nspmv)
+            with open(args.dump_ops, "w") as f:
+                f.write("idx,level,op,alg_bytes,ms,GBps\n")
+                for i in range(len(ms)):
+                    f.write("%d,%d,%s,%d,%.5f,%.1f\n" % (i, lev[i], tags.get(int(kind[i]), str(kind[i])), by[i], ms[i],
+                                                        by[i] / (ms[i] * 1e-3) / 1e9 if ms[i] > 0 else 0.0))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -316,6 +360,8 @@ def main():
     ap.add_argument("--ref-max-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--no-cache", action="store_true")
+    ap.add_argument("--dump-ops", default=None, help="write the per-launch table of one V-cycle (CUDA events) to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
