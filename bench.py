@@ -228,6 +228,9 @@ def run_gpu(args):
     if world > 1:
         raise SystemExit("multi-GPU bench path not available yet")
     pc = pflare_b200.PC(device=local).setType("air").setHierarchy(H)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        pc.setOption(k, float(v))
     t = time.time()
     pc.setUp()
     dev = pc.device()
@@ -361,6 +364,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-cache", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch table of one V-cycle (CUDA events) to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

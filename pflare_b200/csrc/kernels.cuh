@@ -2,14 +2,18 @@
 //
 // One SpMV "mega-op" covers every MatMult + Vec-AXPY chain of the reference's apply path
 // (SURVEY.md section 2c): the CSR product of a row is reduced once and the row epilogue applies
-// the fused vector updates.  The path is HBM-bound fp64/int32 work (no tensor cores by design):
-//   * matrix values / column indices are streamed with coalesced, cache-streaming loads,
-//     a fixed-size nnz tile per CTA ("row blocks" computed once at upload) so every CTA moves
-//     the same number of bytes regardless of row lengths (segment-balanced CSR);
-//   * products are staged in shared memory and each row is reduced by one thread in stored
-//     column order (the reference's MatMult_SeqAIJ summation order);
-//   * x gathers go through L1/L2 (the nested CF layout keeps them near-sequential);
-//   * rows longer than a tile fall back to a whole-CTA reduction.
+// the fused vector updates.  The path is HBM-bound fp64/int32 work (no tensor cores by design).
+//
+//   spmv_tma_kernel     the kernel of the large levels: persistent CTAs, the matrix stream
+//                       (values, column indices, row pointers of a tile) is brought into a
+//                       shared-memory ring by 1-D TMA bulk copies signalled on mbarriers, so the
+//                       HBM stream never drains while a tile is multiplied / reduced; the
+//                       per-row epilogue operands are prefetched into registers before the
+//                       tile's barrier is waited on.
+//   spmv_stream_kernel  the first-generation smem-staged kernel (option kernel=0; A/B baseline).
+//   tail_kernel         single CTA that runs the whole list of ops of the small coarse levels
+//                       back to back with CTA barriers instead of kernel launches.
+//   ew_kernel           diagonal inverses / scalings / permutations.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,9 +21,11 @@
 namespace pfb {
 
 constexpr int kThreads = 256;       // CTA size of the streaming kernels
-constexpr int kTile = 2048;         // nnz per CTA tile (16 KB of fp64 products in smem)
+constexpr int kTile = 2048;         // nnz per CTA tile of the stream / tail kernels (16 KB of fp64 products)
 constexpr int kMaxRowsPerBlk = 1024;
 constexpr int kTailThreads = 1024;  // CTA size of the single-CTA tail kernel
+
+struct TileDesc { int r0, nrows, s, n; };  // first row, #rows, first nnz, #nnz (n > tile size: one long row)
 
 struct SpmvOp {
   // CSR block + its row-block partition
@@ -27,11 +33,11 @@ struct SpmvOp {
   const double *val;
   int m, nblk;
   const int *blk;
+  const TileDesc *tiles;       // tile list of the TMA-pipelined kernel
+  int ntiles;
   // gather sources: column c < nloc reads x[c], otherwise xg[c - nloc] (ghost buffer)
   const double *x, *xg;
   int nloc;
-  const int *rowmap;           // optional: CSR row r updates vector entry rowmap[r]
-  const unsigned char *skip;   // optional: rows with skip[i] != 0 are left to the boundary pass
   // s = sum_j a_ij x_j ; optional s /= D[i] ; optional s = x[i] - s (Neumann I - D^-1 A)
   const double *D;
   int neumann;
@@ -41,8 +47,9 @@ struct SpmvOp {
   double *out; int out_mode;   // 0 none, 1 out[i] = v, 2 out[i] += v
   double *out2; double delta;  // out2[i] = delta * v
   double *acc; double gamma; const double *acc_src; int acc_mode;  // acc[i] (=|+=) gamma * (acc_src ? acc_src[i] : v)
-  // one-point prolongation companion: wout[i] = wcol[i] >= 0 ? wval[i] * x[wcol[i]] : 0
-  const int *wcol; const double *wval; double *wout;
+  // one-point prolongation companion (A_fc|W merged CSR): the LAST stored entry of every row is
+  // the W entry (wval, wcol); its product is not part of the row sum but gives wout[i] = W x_c
+  int wlast; double *wout;
   // fully local F smooth (diagonal A_ff and diagonal inverse): x = wout value; repeat fd_its:
   // x += fd_m[i] * (v - fd_a[i] * x); wout[i] = x
   const double *fd_a, *fd_m; int fd_its;
@@ -72,31 +79,44 @@ __device__ __forceinline__ double gather_x(const SpmvOp &op, int c) {
   return op.x[c];
 }
 
-__device__ __forceinline__ void row_epilogue(const SpmvOp &op, int r, double s) {
-  const int i = op.rowmap ? op.rowmap[r] : r;
-  if (op.skip && op.skip[i]) return;
-  if (op.D) s = s / op.D[i];
-  if (op.neumann) s = op.x[i] - s;
+// Row epilogue, split in two so that the loads that depend only on the row index can be issued
+// long before the row sum exists.
+struct EpiPre { double aux, D, xi, fa, fm, out, accsrc, acc; };
+
+__device__ __forceinline__ EpiPre epi_prefetch(const SpmvOp &op, int i) {
+  EpiPre p;
+  p.aux = op.aux ? op.aux[i] : 0.0;
+  p.D = op.D ? op.D[i] : 1.0;
+  p.xi = op.neumann ? op.x[i] : 0.0;
+  p.fa = op.fd_its > 0 ? op.fd_a[i] : 0.0;
+  p.fm = op.fd_its > 0 ? op.fd_m[i] : 0.0;
+  p.out = op.out_mode == 2 ? op.out[i] : 0.0;
+  p.accsrc = (op.acc_mode && op.acc_src) ? op.acc_src[i] : 0.0;
+  p.acc = op.acc_mode == 2 ? op.acc[i] : 0.0;
+  return p;
+}
+
+__device__ __forceinline__ void epi_finish(const SpmvOp &op, int i, double s, double xw, const EpiPre &p) {
+  if (op.D) s = s / p.D;
+  if (op.neumann) s = p.xi - s;
   double v = op.beta * s;
-  if (op.aux) v = op.alpha * op.aux[i] + v;
+  if (op.aux) v = op.alpha * p.aux + v;
   if (op.wout) {
-    double xw = 0.0;
-    const int wc = op.wcol[i];
-    if (wc >= 0) xw = op.wval[i] * gather_x(op, wc);
-    if (op.fd_its > 0) {
-      const double a = op.fd_a[i], mm = op.fd_m[i];
-      for (int it = 0; it < op.fd_its; ++it) xw = xw + mm * (v - a * xw);
-    }
+    for (int it = 0; it < op.fd_its; ++it) xw = xw + p.fm * (v - p.fa * xw);
     op.wout[i] = xw;
   }
   if (op.out_mode == 1) op.out[i] = v;
-  else if (op.out_mode == 2) op.out[i] += v;
+  else if (op.out_mode == 2) op.out[i] = p.out + v;
   if (op.out2) op.out2[i] = op.delta * v;
   if (op.acc_mode) {
-    const double t = op.gamma * (op.acc_src ? op.acc_src[i] : v);
-    if (op.acc_mode == 1) op.acc[i] = t;
-    else op.acc[i] += t;
+    const double t = op.gamma * (op.acc_src ? p.accsrc : v);
+    op.acc[i] = op.acc_mode == 1 ? t : p.acc + t;
   }
+}
+
+__device__ __forceinline__ void row_epilogue(const SpmvOp &op, int i, double s, double xw) {
+  const EpiPre p = epi_prefetch(op, i);
+  epi_finish(op, i, s, xw, p);
 }
 
 // Process one row block with all threads of the CTA.  `prod` holds kTile doubles.
@@ -121,16 +141,19 @@ __device__ __forceinline__ void process_block(const SpmvOp &op, int b, double *p
     __syncthreads();
     for (int r = r0 + tid; r < r1; r += NT) {
       int p = __ldg(op.rp + r) - s;
-      const int q = __ldg(op.rp + r + 1) - s;
+      int q = __ldg(op.rp + r + 1) - s;
+      double xw = 0.0;
+      if (op.wlast) { --q; xw = prod[q]; }
       double sum = 0.0;
       for (; p < q; ++p) sum += prod[p];
-      row_epilogue(op, r, sum);
+      row_epilogue(op, r, sum, xw);
     }
     __syncthreads();
   } else {
     // a single long row: whole-CTA reduction
+    const int last = op.wlast ? e - 1 : e;
     double part = 0.0;
-    for (int k = s + tid; k < e; k += NT) part += ld_stream(op.val + k) * gather_x(op, ld_stream(op.col + k));
+    for (int k = s + tid; k < last; k += NT) part += ld_stream(op.val + k) * gather_x(op, ld_stream(op.col + k));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if ((tid & 31) == 0) red[tid >> 5] = part;
@@ -138,7 +161,8 @@ __device__ __forceinline__ void process_block(const SpmvOp &op, int b, double *p
     if (tid == 0) {
       double sum = 0.0;
       for (int w = 0; w < NT / 32; ++w) sum += red[w];
-      row_epilogue(op, r0, sum);
+      const double xw = op.wlast ? op.val[last] * gather_x(op, op.col[last]) : 0.0;
+      row_epilogue(op, r0, sum, xw);
     }
     __syncthreads();
   }
@@ -148,6 +172,189 @@ __global__ void __launch_bounds__(kThreads) spmv_stream_kernel(const SpmvOp op) 
   __shared__ double prod[kTile];
   __shared__ double red[kThreads / 32];
   for (int b = blockIdx.x; b < op.nblk; b += gridDim.x) process_block<kThreads>(op, b, prod, red);
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA-pipelined streaming SpMV (the kernel of the large levels).
+//
+// A persistent CTA walks its tiles (tile = consecutive rows holding <= TILE nonzeros and <= NT
+// rows, fixed at upload).  For every tile ONE elected thread issues three 1-D bulk copies
+// (cp.async.bulk, the TMA engine: SASS UBLKCP) that bring the tile's values, column indices and
+// row pointers into a STAGES-deep shared-memory ring; completion is signalled on an mbarrier per
+// stage.  While tile t is being multiplied/reduced, tiles t+1 .. t+STAGES-1 are in flight, so the
+// HBM stream does not drain at the barriers of the multiply/reduce phases.  Every thread owns at
+// most one row of the tile and issues the loads of that row's epilogue operands BEFORE it waits
+// for the tile, so the reduce phase touches no global-memory latency.  x is gathered with
+// ordinary loads (L1/L2; the nested CF ordering keeps the gathers near-sequential).
+//
+// Bulk copies need 16-byte aligned addresses and sizes: the copy starts at the tile's first
+// nonzero rounded DOWN to a multiple of 4 entries and is rounded UP to a multiple of 4 (the
+// arrays are over-allocated by a few entries at upload).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// The matrix stream is read exactly once per op: mark it evict-first in L2 so that it does not
+// push the gathered vectors (which ARE re-read, by neighbouring rows and by the next op) out of
+// the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+
+template <int TILE, int MAXROWS>
+struct TmaStage {
+  double val[TILE + 8];
+  int col[TILE + 8];
+  int rp[MAXROWS + 8];
+};
+
+template <int NT, int TILE, int STAGES, bool ROWMAP>
+__global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  typedef TmaStage<TILE, NT> Stage;
+  Stage *stages = reinterpret_cast<Stage *>(smem_raw);
+  __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ TileDesc sdesc[STAGES];
+  __shared__ double red[NT / 32 + 1];
+  const int tid = threadIdx.x;
+  const TileDesc *__restrict__ tiles = op.tiles;
+  const int ntiles = op.ntiles;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_tiles = (first < ntiles) ? (ntiles - first + stride - 1) / stride : 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint64_t pol = l2_policy_evict_first();
+  // producer (thread 0): issue the bulk copies of local tile j into ring slot j % STAGES
+  auto issue = [&](int j) {
+    const TileDesc d = tiles[first + j * stride];
+    const int slot = j % STAGES;
+    sdesc[slot] = d;
+    if (d.n <= TILE) {
+      Stage &S = stages[slot];
+      const int s_al = d.s & ~3;
+      const int cnt = (d.n + (d.s - s_al) + 3) & ~3;
+      const int r_al = d.r0 & ~3;
+      const int rcnt = (d.nrows + 1 + (d.r0 - r_al) + 3) & ~3;
+      mbar_expect_tx(&full[slot], (uint32_t)(cnt * 12 + rcnt * 4));
+      tma_load_1d(S.val, op.val + s_al, (uint32_t)(cnt * 8), &full[slot], pol);
+      tma_load_1d(S.col, op.col + s_al, (uint32_t)(cnt * 4), &full[slot], pol);
+      tma_load_1d(S.rp, op.rp + r_al, (uint32_t)(rcnt * 4), &full[slot], pol);
+    } else {
+      mbar_expect_tx(&full[slot], 0);  // long row: streamed straight from global by the whole CTA
+    }
+  };
+  if (tid == 0) {
+    for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);
+  }
+  __syncthreads();
+
+  for (int it = 0; it < my_tiles; ++it) {
+    const int slot = it % STAGES;
+    if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);  // slot freed by the barrier ending iteration it-1
+    const TileDesc d = sdesc[slot];
+    Stage &S = stages[slot];
+    if (d.n <= TILE) {
+      // operands of my row's epilogue: in flight while the tile lands and is multiplied
+      int g = 1;
+      if (ROWMAP) {
+        while (g < 32 && d.nrows * (g << 1) <= NT) g <<= 1;
+      }
+      const bool has_row = ROWMAP ? (tid < d.nrows * g && (tid & (g - 1)) == 0) : (tid < d.nrows);
+      EpiPre pre;
+      if (has_row) pre = epi_prefetch(op, d.r0 + (ROWMAP ? tid / g : tid));
+      mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
+      const int o = d.s & 3;
+      if (ROWMAP) {
+        // g lanes per row (g = largest power of two with nrows * g <= NT, at most 32): lanes of
+        // neighbouring rows gather neighbouring x entries, so a warp's gather touches few lines
+        const bool active = tid < d.nrows * g;
+        const int row = tid / g, lg = tid & (g - 1);
+        int p = 0, q = 0;
+        if (active) {
+          const int ro = d.r0 & 3;
+          p = S.rp[ro + row] - d.s + o;
+          q = S.rp[ro + row + 1] - d.s + o;
+        }
+        const int qs = op.wlast ? q - 1 : q;
+        double sum = 0.0, xw = 0.0;
+        for (int k = p + lg; k < qs; k += g) sum += S.val[k] * gather_x(op, S.col[k]);
+        if (op.wlast && active && lg == ((qs - p) & (g - 1))) xw = S.val[qs] * gather_x(op, S.col[qs]);
+        for (int w = g >> 1; w > 0; w >>= 1) {   // all lanes of the warp take part (inactive ones carry zeros)
+          sum += __shfl_down_sync(0xffffffffu, sum, w, g);
+          if (op.wlast) xw += __shfl_down_sync(0xffffffffu, xw, w, g);
+        }
+        if (active && lg == 0) epi_finish(op, d.r0 + row, sum, xw, pre);
+      } else {
+        constexpr int kIter = TILE / NT;
+#pragma unroll
+        for (int k0 = 0; k0 < kIter; ++k0) {
+          const int k = tid + k0 * NT;
+          if (k < d.n) {
+            const int c = S.col[o + k];
+            S.val[o + k] = S.val[o + k] * gather_x(op, c);
+          }
+        }
+        __syncthreads();
+        if (has_row) {
+          const int ro = d.r0 & 3;
+          int p = S.rp[ro + tid] - d.s + o;
+          int q = S.rp[ro + tid + 1] - d.s + o;
+          double xw = 0.0;
+          if (op.wlast) { --q; xw = S.val[q]; }
+          double sum = 0.0;
+          for (; p < q; ++p) sum += S.val[p];
+          epi_finish(op, d.r0 + tid, sum, xw, pre);
+        }
+      }
+    } else {
+      mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
+      const int e = d.s + d.n;
+      const int last = op.wlast ? e - 1 : e;
+      double part = 0.0;
+      for (int k = d.s + tid; k < last; k += NT) part += ld_stream(op.val + k) * gather_x(op, ld_stream(op.col + k));
+#pragma unroll
+      for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(0xffffffffu, part, w);
+      if ((tid & 31) == 0) red[tid >> 5] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < NT / 32; ++w) sum += red[w];
+        const double xw = op.wlast ? op.val[last] * gather_x(op, op.col[last]) : 0.0;
+        row_epilogue(op, d.r0, sum, xw);
+      }
+    }
+    // generic-proxy accesses to this slot are done; order them before the next bulk copy into it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
 }
 
 __device__ __forceinline__ void ew_apply(const EwOp &e, int i) {

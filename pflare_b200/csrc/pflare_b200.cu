@@ -56,6 +56,12 @@ int fail(int code, const char *fmt, ...) {
 // PFLARE_TOL_ZERO: single-precision literal 1e-12 widened to double (src/Pflare_Parameters.F90:206)
 const double kTolZero = (double)1e-12f;
 
+// TMA-pipelined kernel variants: {threads (= max rows per tile), nnz per tile, pipeline stages}
+struct Variant { int nt, tile, stages; };
+const Variant kVariants[] = {{0, 0, 0}, {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {256, 2048, 3}, {512, 2048, 2}, {512, 4096, 2}, {128, 512, 3}, {128, 1024, 4},
+                             {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {512, 2048, 2}, {128, 512, 3}};  // 9..13: row-mapped multiply
+const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+
 struct HostCSR {
   bool set = false;
   int m = 0, n = 0;
@@ -74,10 +80,13 @@ struct DevCSR {
   int m = 0, n = 0;
   int64_t nnz = 0;
   int64_t nx = 0;  // distinct columns referenced (byte model)
+  int64_t nnz_model = -1;  // nnz counted by the reference's work model when it differs from nnz
   int *rp = nullptr, *col = nullptr;
   double *val = nullptr;
   int nblk = 0;
   int *blk = nullptr;
+  int ntiles = 0;
+  TileDesc *tiles = nullptr;
   bool valid() const { return rp != nullptr; }
 };
 
@@ -99,9 +108,7 @@ struct Level {
   HostCSR H[9];
   Inv inv_ff, inv_cc;
   // device
-  DevCSR Z, W, Afc, Aff, Acf, Acc, Coarse;
-  int *wcol = nullptr;
-  double *wval = nullptr;
+  DevCSR Z, W, Afc, Afcw, Aff, Acf, Acc, Coarse;   // Afcw = A_fc with the one-point W entry appended to every row
   bool w_onepoint = false;
   bool aff_diag_only = false;
   double *aff_diag = nullptr;  // diagonal of A_ff (F-local order): MF_VEC_DIAG and the fused local smooth
@@ -149,6 +156,9 @@ struct Ctx {
   int use_graph = 1, fuse = 1;
   int tail_rows = 2048;
   int64_t tail_nnz = 40000;
+  int kernel = 1;        // 0: smem-staged stream kernel, 1..: TMA-pipelined variants (kVariants)
+  int tile_kernel = 1;   // the variant the uploaded tile lists were built for
+  int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int num_sms = 148;
   std::unique_ptr<Comm> comm;
 };
@@ -174,21 +184,31 @@ int dev_upload(Ctx *c, T **p, const std::vector<T> &v) {
 
 // Row-block partition: consecutive rows with <= kTile nnz and <= kMaxRowsPerBlk rows per block;
 // a row longer than kTile forms its own block.
-std::vector<int> make_blocks(const std::vector<int> &ia, int m) {
+std::vector<int> make_blocks(const std::vector<int> &ia, int m, int tile = kTile, int maxrows = kMaxRowsPerBlk) {
   std::vector<int> blk;
   blk.push_back(0);
   int r = 0;
   while (r < m) {
     int r0 = r;
     int64_t base = ia[r0];
-    if (ia[r0 + 1] - base > kTile) {
+    if (ia[r0 + 1] - base > tile) {
       r = r0 + 1;
     } else {
-      while (r < m && (r - r0) < kMaxRowsPerBlk && ia[r + 1] - base <= kTile) ++r;
+      while (r < m && (r - r0) < maxrows && ia[r + 1] - base <= tile) ++r;
     }
     blk.push_back(r);
   }
   return blk;
+}
+
+// over-allocating upload: the TMA kernel's bulk copies round their extent up to 16 bytes
+template <class T>
+int dev_upload_padded(Ctx *c, T **p, const std::vector<T> &v, size_t pad) {
+  int rc = dev_alloc(c, p, v.size() + pad);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemset(*p, 0, (v.size() + pad) * sizeof(T)));
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
 }
 
 int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d) {
@@ -202,12 +222,18 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d) {
     if (!seen[cidx]) { seen[cidx] = 1; ++nx; }
   d->nx = nx;
   int rc;
-  if ((rc = dev_upload(c, &d->rp, h.ia))) return rc;
-  if ((rc = dev_upload(c, &d->col, h.ja))) return rc;
-  if ((rc = dev_upload(c, &d->val, h.a))) return rc;
+  if ((rc = dev_upload_padded(c, &d->rp, h.ia, 8))) return rc;
+  if ((rc = dev_upload_padded(c, &d->col, h.ja, 8))) return rc;
+  if ((rc = dev_upload_padded(c, &d->val, h.a, 8))) return rc;
   std::vector<int> blk = make_blocks(h.ia, h.m);
   d->nblk = (int)blk.size() - 1;
   if ((rc = dev_upload(c, &d->blk, blk))) return rc;
+  const Variant &V = kVariants[c->tile_kernel];
+  std::vector<int> tb = make_blocks(h.ia, h.m, V.tile, V.nt);
+  std::vector<TileDesc> tiles(tb.size() - 1);
+  for (size_t t = 0; t + 1 < tb.size(); ++t) tiles[t] = TileDesc{tb[t], tb[t + 1] - tb[t], h.ia[tb[t]], h.ia[tb[t + 1]] - h.ia[tb[t]]};
+  d->ntiles = (int)tiles.size();
+  if ((rc = dev_upload(c, &d->tiles, tiles))) return rc;
   return 0;
 }
 
@@ -279,6 +305,7 @@ struct Builder {
   SpmvOp base(const DevCSR &A, const double *x) {
     SpmvOp s{};
     s.rp = A.rp; s.col = A.col; s.val = A.val; s.m = A.m; s.nblk = A.nblk; s.blk = A.blk;
+    s.tiles = A.tiles; s.ntiles = A.ntiles;
     s.x = x; s.nloc = A.n; s.beta = 1.0;
     return s;
   }
@@ -286,7 +313,7 @@ struct Builder {
     Op o;
     o.kind = OPK_SPMV; o.s = s; o.level = level; o.tag = tag;
     o.bytes = spmv_bytes(A, aux_reads, w) + extra_bytes;
-    o.nnz = (double)A.nnz;
+    o.nnz = (double)(A.nnz_model >= 0 ? A.nnz_model : A.nnz);
     out->push_back(o);
   }
   // out (=|+=) alpha * a .* b ./ dv
@@ -406,10 +433,6 @@ struct Builder {
 
   // x_f = W x_c as its own op (used when the first smoothing run is not an F smooth)
   void emit_prolong(Level &Lv, double *xf, const double *xc) {
-    if (Lv.w_onepoint) {
-      // gather: x_f[i] = wval[i] * x_c[wcol[i]]; expressed through the SpMV op on an empty block is
-      // not possible, so use the stored CSR form of W
-    }
     SpmvOp s = base(Lv.W, xc);
     s.out = xf; s.out_mode = 1;
     push_spmv(s, Lv.W, 3, 0, 1);
@@ -426,18 +449,21 @@ struct Builder {
     // fully local variant: A_ff diagonal and diagonal inverse -> the whole F smooth is row-local
     const bool local = c->fuse && fuse_w && Lv.aff_diag_only && Lv.inv_ff.kind == 2;
     {
-      SpmvOp s = base(Lv.Afc, xc);  // rhs = b_f - A_fc x_c   (src/FC_Smooth.F90:533-538)
+      // rhs = b_f - A_fc x_c (src/FC_Smooth.F90:533-538); with the fused one-point prolongation the
+      // merged A_fc|W operator also produces x_f = W x_c (MatInterpolate) from the same gathers
+      const DevCSR &A = fuse_w ? Lv.Afcw : Lv.Afc;
+      SpmvOp s = base(A, xc);
       s.aux = bf; s.alpha = 1.0; s.beta = -1.0;
       double extra = 0;
-      if (fuse_w) { s.wcol = Lv.wcol; s.wval = Lv.wval; s.wout = xf; extra += 12.0 * Lv.nf + 8.0 * Lv.nf; }
+      if (fuse_w) { s.wlast = 1; s.wout = xf; extra += 8.0 * Lv.nf; }
       if (local) {
         s.fd_a = Lv.aff_diag; s.fd_m = Lv.inv_ff.ddiag; s.fd_its = its;
         extra += 16.0 * Lv.nf;
-        push_spmv(s, Lv.Afc, 7, 1, 0, extra);
+        push_spmv(s, A, 7, 1, 0, extra);
         return 0;
       }
       s.out = S[0]; s.out_mode = 1;
-      push_spmv(s, Lv.Afc, 3, 1, 1, extra);
+      push_spmv(s, A, 3, 1, 1, extra);
     }
     for (int f = 0; f < its; ++f) {
       SpmvOp s = base(Lv.Aff, xf);  // r = rhs - A_ff x_f     (src/FC_Smooth.F90:544-549)
@@ -489,12 +515,55 @@ struct Builder {
   }
 };
 
-int launch_op(Ctx *c, const Op &o, cudaStream_t st) {
+template <int NT, int TILE, int STAGES, bool ROWMAP = false>
+int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  auto kern = spmv_tma_kernel<NT, TILE, STAGES, ROWMAP>;
+  const size_t smem = sizeof(TmaStage<TILE, NT>) * STAGES;
+  static int per_sm = 0;   // resident CTAs per SM of this instantiation (occupancy calculator, once)
+  if (per_sm == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem));
+    per_sm = std::max(nb, 1);
+  }
+  if (dry) return 0;
+  const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
+  const int grid = std::min(s.ntiles, c->num_sms * want);   // persistent: a multiple of the SM count
+  kern<<<grid, NT, smem, st>>>(s);
+  return 0;
+}
+
+int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
   if (o.kind == OPK_SPMV) {
-    if (o.s.m == 0 || o.s.nblk == 0) return 0;
-    int grid = std::min(o.s.nblk, c->num_sms * 8 * 4);
-    spmv_stream_kernel<<<grid, kThreads, 0, st>>>(o.s);
+    if (!dry && (o.s.m == 0 || o.s.nblk == 0)) return 0;
+    int rc = 0;
+    const int k = c->kernel;
+    switch (k) {
+      case 0: {
+        if (dry) return 0;
+        int grid = std::min(o.s.nblk, c->num_sms * 8 * 4);
+        spmv_stream_kernel<<<grid, kThreads, 0, st>>>(o.s);
+        break;
+      }
+      case 1: rc = launch_tma<256, 1024, 2>(c, o.s, st, dry); break;
+      case 2: rc = launch_tma<256, 1024, 3>(c, o.s, st, dry); break;
+      case 3: rc = launch_tma<256, 2048, 2>(c, o.s, st, dry); break;
+      case 4: rc = launch_tma<256, 2048, 3>(c, o.s, st, dry); break;
+      case 5: rc = launch_tma<512, 2048, 2>(c, o.s, st, dry); break;
+      case 6: rc = launch_tma<512, 4096, 2>(c, o.s, st, dry); break;
+      case 7: rc = launch_tma<128, 512, 3>(c, o.s, st, dry); break;
+      case 8: rc = launch_tma<128, 1024, 4>(c, o.s, st, dry); break;
+      case 9: rc = launch_tma<256, 1024, 2, true>(c, o.s, st, dry); break;
+      case 10: rc = launch_tma<256, 1024, 3, true>(c, o.s, st, dry); break;
+      case 11: rc = launch_tma<256, 2048, 2, true>(c, o.s, st, dry); break;
+      case 12: rc = launch_tma<512, 2048, 2, true>(c, o.s, st, dry); break;
+      case 13: rc = launch_tma<128, 512, 3, true>(c, o.s, st, dry); break;
+      default: return fail(2, "unknown kernel variant %d", k);
+    }
+    if (rc) return rc;
+    if (dry) return 0;
   } else {
+    if (dry) return 0;
     if (o.e.n == 0) return 0;
     int grid = std::min((o.e.n + kThreads - 1) / kThreads, c->num_sms * 8);
     ew_kernel<<<grid, kThreads, 0, st>>>(o.e);
@@ -525,6 +594,11 @@ int run_program(Ctx *c, cudaStream_t st, int *nkernels) {
 }
 
 int build_graph(Ctx *c) {
+  {  // kernel attributes / occupancy of the selected SpMV variant, outside the capture
+    Op dummy;
+    int rc0 = launch_op(c, dummy, c->stream, true);
+    if (rc0) return rc0;
+  }
   if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
   if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
   CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -549,7 +623,7 @@ int build_program(Ctx *c) {
   for (int l = NL; l >= 1; --l) {
     Level &Lv = c->L[l];
     int64_t mx = 0;
-    for (const DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.inv_ff.d, &Lv.inv_cc.d}) mx = std::max(mx, A->nnz);
+    for (const DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.inv_ff.d, &Lv.inv_cc.d}) mx = std::max(mx, A->nnz);
     if (Lv.n <= c->tail_rows && mx <= c->tail_nnz) ltail = l; else break;
   }
   c->tail_levels = (ltail <= NL) ? NL - ltail + 1 : 0;
@@ -799,20 +873,26 @@ int pflare_b200_finalize_setup(void *handle) {
       HostCSR W = remap(Wn, nullptr, pc.data(), Lv.nc);
       if ((rc = upload_csr(c, W, &Lv.W))) return rc;
       Lv.w_onepoint = onept;
-      if (onept) {
-        std::vector<int> wc((size_t)Lv.nf, -1);
-        std::vector<double> wv((size_t)Lv.nf, 0.0);
-        for (int j = 0; j < Lv.nf; ++j)
-          if (W.ia[j + 1] > W.ia[j]) { wc[j] = W.ja[W.ia[j]]; wv[j] = W.a[W.ia[j]]; }
-        if ((rc = dev_upload(c, &Lv.wcol, wc))) return rc;
-        if ((rc = dev_upload(c, &Lv.wval, wv))) return rc;
-      }
       // A_fc, A_ff
       const HostCSR &Afc = Lv.H[PFLARE_B200_AFC], &Aff = Lv.H[PFLARE_B200_AFF];
       if (!Afc.set || Afc.m != Lv.nf || Afc.n != Lv.nc) return fail(2, "level %d: A_fc missing or wrong shape", l);
       if (!Aff.set || Aff.m != Lv.nf || Aff.n != Lv.nf) return fail(2, "level %d: A_ff missing or wrong shape", l);
       HostCSR Afc2 = remap(Afc, nullptr, pc.data(), Lv.nc);
       if ((rc = upload_csr(c, Afc2, &Lv.Afc))) return rc;
+      if (onept) {
+        // merged A_fc|W: every row gets its W entry (or an explicit 0.0 * x_c[0]) appended as LAST entry
+        HostCSR M; M.set = true; M.m = Lv.nf; M.n = Lv.nc; M.ia.assign((size_t)Lv.nf + 1, 0);
+        for (int j = 0; j < Lv.nf; ++j) M.ia[j + 1] = M.ia[j] + (Afc2.ia[j + 1] - Afc2.ia[j]) + 1;
+        M.ja.resize((size_t)M.ia[Lv.nf]); M.a.resize((size_t)M.ia[Lv.nf]);
+        for (int j = 0; j < Lv.nf; ++j) {
+          int o = M.ia[j];
+          for (int p = Afc2.ia[j]; p < Afc2.ia[j + 1]; ++p) { M.ja[o] = Afc2.ja[p]; M.a[o] = Afc2.a[p]; ++o; }
+          if (W.ia[j + 1] > W.ia[j]) { M.ja[o] = W.ja[W.ia[j]]; M.a[o] = W.a[W.ia[j]]; }
+          else { M.ja[o] = 0; M.a[o] = 0.0; }
+        }
+        if ((rc = upload_csr(c, M, &Lv.Afcw))) return rc;
+        Lv.Afcw.nnz_model = Afc2.nnz() + W.nnz();
+      }
       if ((rc = upload_csr(c, Aff, &Lv.Aff))) return rc;
       Lv.aff_diag_only = is_diag_only(Aff);
       if ((rc = dev_upload(c, &Lv.aff_diag, extract_diag(Aff)))) return rc;
@@ -1096,6 +1176,14 @@ int pflare_b200_set_option(void *handle, const char *key, double value) {
   else if (k == "fuse") c->fuse = value != 0;
   else if (k == "tail_rows") c->tail_rows = (int)value;
   else if (k == "tail_nnz") c->tail_nnz = (int64_t)value;
+  else if (k == "kernel") {
+    const int v = (int)value;
+    if (v < 0 || v >= kNumVariants) return fail(2, "kernel variant must be 0..%d", kNumVariants - 1);
+    if (c->finalized && v != 0 && v != c->tile_kernel) return fail(2, "kernel variant %d needs other tile lists: set it before finalize_setup", v);
+    c->kernel = v;
+    if (!c->finalized && v != 0) c->tile_kernel = v;
+  }
+  else if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->finalized) {
     if ((rc = build_program(c))) return rc;

@@ -49,7 +49,15 @@ def test_vcycle_parity(built_libs, name):
 
 
 @pytest.mark.parametrize("opts", [dict(graph=0), dict(tail_rows=0), dict(fuse=0), dict(tail_rows=100000, tail_nnz=1e9),
-                                  dict(graph=0, fuse=0, tail_rows=0)])
+                                  dict(graph=0, fuse=0, tail_rows=0),
+                                  # SpMV kernel variants: 0 = smem-staged stream kernel, 1.. = TMA-pipelined (stages / tile sizes)
+                                  dict(kernel=0, tail_rows=0), dict(kernel=1, tail_rows=0), dict(kernel=2, tail_rows=0),
+                                  dict(kernel=3, tail_rows=0), dict(kernel=4, tail_rows=0), dict(kernel=5, tail_rows=0),
+                                  dict(kernel=6, tail_rows=0), dict(kernel=7, tail_rows=0), dict(kernel=8, tail_rows=0),
+                                  dict(kernel=9, tail_rows=0), dict(kernel=10, tail_rows=0), dict(kernel=11, tail_rows=0),
+                                  dict(kernel=12, tail_rows=0), dict(kernel=13, tail_rows=0),
+                                  dict(kernel=2, ctas_per_sm=1)],
+                         ids=lambda o: ",".join("%s=%g" % kv for kv in o.items()))
 @pytest.mark.parametrize("name", ["fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "fd2d_diagAff", "dg_mf", "fd2d_idealW"])
 def test_vcycle_parity_execution_modes(built_libs, name, opts):
     A, H = cases.build(name)
