@@ -53,6 +53,7 @@ struct SpmvOp {
   // fully local F smooth (diagonal A_ff and diagonal inverse): x = wout value; repeat fd_its:
   // x += fd_m[i] * (v - fd_a[i] * x); wout[i] = x
   const double *fd_a, *fd_m; int fd_its;
+  int dbg_seq;                 // measurement only: gather x sequentially instead of through col (wrong results)
 };
 
 // out[i] (=|+=) alpha * a[i] * (b ? b[i] : 1) / (dv ? dv[i] : 1)
@@ -231,8 +232,8 @@ struct TmaStage {
   int rp[MAXROWS + 8];
 };
 
-template <int NT, int TILE, int STAGES, bool ROWMAP>
-__global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
+template <int NT, int TILE, int STAGES, bool ROWMAP, int MINB>
+__global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef TmaStage<TILE, NT> Stage;
   Stage *stages = reinterpret_cast<Stage *>(smem_raw);
@@ -253,8 +254,13 @@ __global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
 
   const uint64_t pol = l2_policy_evict_first();
   // producer (thread 0): issue the bulk copies of local tile j into ring slot j % STAGES
+  // (the descriptor of the NEXT tile is fetched one issue ahead so the elected thread never
+  // stalls on a global load between a tile's barrier and the next bulk copy)
+  TileDesc dnext = {0, 0, 0, 0};
+  if (tid == 0 && my_tiles > 0) dnext = tiles[first];
   auto issue = [&](int j) {
-    const TileDesc d = tiles[first + j * stride];
+    const TileDesc d = dnext;
+    if (j + 1 < my_tiles) dnext = tiles[first + (j + 1) * stride];
     const int slot = j % STAGES;
     sdesc[slot] = d;
     if (d.n <= TILE) {
@@ -278,8 +284,11 @@ __global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
 
   for (int it = 0; it < my_tiles; ++it) {
     const int slot = it % STAGES;
-    if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);  // slot freed by the barrier ending iteration it-1
     const TileDesc d = sdesc[slot];
+    // when to issue the bulk copies of tile it+STAGES-1 (its slot was freed by the barrier ending
+    // iteration it-1): normally right after this tile's gathers have been queued
+    const bool late_issue = !ROWMAP && op.dbg_seq != 6 && op.dbg_seq != 2 && d.n <= TILE;
+    if (!late_issue && tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
     Stage &S = stages[slot];
     if (d.n <= TILE) {
       // operands of my row's epilogue: in flight while the tile lands and is multiplied
@@ -289,9 +298,15 @@ __global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
       }
       const bool has_row = ROWMAP ? (tid < d.nrows * g && (tid & (g - 1)) == 0) : (tid < d.nrows);
       EpiPre pre;
-      if (has_row) pre = epi_prefetch(op, d.r0 + (ROWMAP ? tid / g : tid));
+      if (has_row && op.dbg_seq != 2 && op.dbg_seq != 5) pre = epi_prefetch(op, d.r0 + (ROWMAP ? tid / g : tid));
       mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
       const int o = d.s & 3;
+      if (op.dbg_seq == 2) {  // measurement only: TMA stream + barriers, no work
+        if (tid == 0 && S.val[o] == 1.2345e300) op.out[0] = 0.0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        continue;
+      }
       if (ROWMAP) {
         // g lanes per row (g = largest power of two with nrows * g <= NT, at most 32): lanes of
         // neighbouring rows gather neighbouring x entries, so a warp's gather touches few lines
@@ -314,13 +329,24 @@ __global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
         if (active && lg == 0) epi_finish(op, d.r0 + row, sum, xw, pre);
       } else {
         constexpr int kIter = TILE / NT;
+        double xr[kIter];
 #pragma unroll
         for (int k0 = 0; k0 < kIter; ++k0) {
           const int k = tid + k0 * NT;
+          xr[k0] = 0.0;
           if (k < d.n) {
-            const int c = S.col[o + k];
-            S.val[o + k] = S.val[o + k] * gather_x(op, c);
+            int c = S.col[o + k];
+            if (op.dbg_seq == 1) c = (d.r0 + k) % op.nloc;
+            if (op.dbg_seq >= 3 && op.dbg_seq <= 5) xr[k0] = (double)c;   // measurement only: no gather
+            else xr[k0] = gather_x(op, c);
           }
+        }
+        // the latency-critical gathers of THIS tile are queued ahead of the next tile's bulk copies
+        if (late_issue && tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
+#pragma unroll
+        for (int k0 = 0; k0 < kIter; ++k0) {
+          const int k = tid + k0 * NT;
+          if (k < d.n) S.val[o + k] = S.val[o + k] * xr[k0];
         }
         __syncthreads();
         if (has_row) {
@@ -331,7 +357,8 @@ __global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
           if (op.wlast) { --q; xw = S.val[q]; }
           double sum = 0.0;
           for (; p < q; ++p) sum += S.val[p];
-          epi_finish(op, d.r0 + tid, sum, xw, pre);
+          if (op.dbg_seq == 5) { if (sum == 1.2345e300) op.out[0] = 0.0; }   // measurement only: no epilogue
+          else epi_finish(op, d.r0 + tid, sum, xw, pre);
         }
       }
     } else {

@@ -59,7 +59,8 @@ const double kTolZero = (double)1e-12f;
 // TMA-pipelined kernel variants: {threads (= max rows per tile), nnz per tile, pipeline stages}
 struct Variant { int nt, tile, stages; };
 const Variant kVariants[] = {{0, 0, 0}, {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {256, 2048, 3}, {512, 2048, 2}, {512, 4096, 2}, {128, 512, 3}, {128, 1024, 4},
-                             {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {512, 2048, 2}, {128, 512, 3}};  // 9..13: row-mapped multiply
+                             {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {512, 2048, 2}, {128, 512, 3},   // 9..13: row-mapped multiply
+                             {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 3}, {128, 512, 2}, {128, 512, 3}};  // 14..19: register-capped for more resident CTAs
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
 struct HostCSR {
@@ -159,6 +160,7 @@ struct Ctx {
   int kernel = 1;        // 0: smem-staged stream kernel, 1..: TMA-pipelined variants (kVariants)
   int tile_kernel = 1;   // the variant the uploaded tile lists were built for
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
+  int dbg_seq = 0;       // measurement only (wrong results): sequential instead of indexed x gathers
   int num_sms = 148;
   std::unique_ptr<Comm> comm;
 };
@@ -305,7 +307,7 @@ struct Builder {
   SpmvOp base(const DevCSR &A, const double *x) {
     SpmvOp s{};
     s.rp = A.rp; s.col = A.col; s.val = A.val; s.m = A.m; s.nblk = A.nblk; s.blk = A.blk;
-    s.tiles = A.tiles; s.ntiles = A.ntiles;
+    s.tiles = A.tiles; s.ntiles = A.ntiles; s.dbg_seq = c->dbg_seq;
     s.x = x; s.nloc = A.n; s.beta = 1.0;
     return s;
   }
@@ -515,9 +517,9 @@ struct Builder {
   }
 };
 
-template <int NT, int TILE, int STAGES, bool ROWMAP = false>
+template <int NT, int TILE, int STAGES, bool ROWMAP = false, int MINB = 1>
 int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_tma_kernel<NT, TILE, STAGES, ROWMAP>;
+  auto kern = spmv_tma_kernel<NT, TILE, STAGES, ROWMAP, MINB>;
   const size_t smem = sizeof(TmaStage<TILE, NT>) * STAGES;
   static int per_sm = 0;   // resident CTAs per SM of this instantiation (occupancy calculator, once)
   if (per_sm == 0) {
@@ -558,6 +560,12 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
       case 11: rc = launch_tma<256, 2048, 2, true>(c, o.s, st, dry); break;
       case 12: rc = launch_tma<512, 2048, 2, true>(c, o.s, st, dry); break;
       case 13: rc = launch_tma<128, 512, 3, true>(c, o.s, st, dry); break;
+      case 14: rc = launch_tma<256, 1024, 2, false, 5>(c, o.s, st, dry); break;
+      case 15: rc = launch_tma<256, 1024, 2, false, 6>(c, o.s, st, dry); break;
+      case 16: rc = launch_tma<256, 1024, 2, false, 8>(c, o.s, st, dry); break;
+      case 17: rc = launch_tma<256, 1024, 3, false, 5>(c, o.s, st, dry); break;
+      case 18: rc = launch_tma<128, 512, 2, false, 16>(c, o.s, st, dry); break;
+      case 19: rc = launch_tma<128, 512, 3, false, 12>(c, o.s, st, dry); break;
       default: return fail(2, "unknown kernel variant %d", k);
     }
     if (rc) return rc;
@@ -1184,6 +1192,7 @@ int pflare_b200_set_option(void *handle, const char *key, double value) {
     if (!c->finalized && v != 0) c->tile_kernel = v;
   }
   else if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
+  else if (k == "dbg_seq_gather") c->dbg_seq = (int)value;
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->finalized) {
     if ((rc = build_program(c))) return rc;
