@@ -15,3 +15,4 @@ and the CUDA path consume.
 from .problems import adv_1d, adv_diff_fd, dg_upwind_surrogate, read_petsc_binary, parilu_factors  # noqa: F401
 from .setup import AirOptions, Hierarchy, Level, Inverse, build_hierarchy, build_pflareinv  # noqa: F401
 from .upload import feed  # noqa: F401
+from .partition import partition, split_ownership, scatter_vector, LocalHierarchy  # noqa: F401

@@ -78,6 +78,17 @@ int pflare_b200_get_unique_id(void *id);
  *   no_levels   : air_data%no_levels (1 for PCPFLAREINV). */
 int pflare_b200_create(void **handle, int rank, int nranks, const void *unique_id, int device, int no_levels);
 
+/* Setup-time host communicator (multi-rank only).  By default the ranks exchange their setup
+ * data (ownership ranges, ghost requests, agglomerated coarse levels) over NCCL; a host program that
+ * already owns an MPI communicator (a PETSc build: the PC's comm) hands it in as two callbacks with
+ * MPI_Alltoall / MPI_Alltoallv semantics on bytes, both returning 0 on success:
+ *   int alltoall (void *ctx, const int64_t *send, int64_t *recv);                 one int64 per rank
+ *   int alltoallv(void *ctx, const char *sbuf, const int64_t *scnt, const int64_t *sdsp,
+ *                 char *rbuf, const int64_t *rcnt, const int64_t *rdsp);
+ * With callbacks set, a context created with device == -1 can run finalize_setup WITHOUT a GPU: it
+ * builds the ghost plans and the kernel program only ("planning context"; apply fails loudly). */
+int pflare_b200_set_host_exchange(void *handle, void *alltoall_fn, void *alltoallv_fn, void *ctx);
+
 /* Per-level metadata.  is_fine / is_coarse are the LOCAL (global - rstart) sorted index lists
  * of IS_fine_index / IS_coarse_index (src/VecISCopyLocalk.kokkos.cxx:73-132); smooth_order is
  * smooth_order_levels(our_level)%array (+k = k F smooths, -k = k C smooths, 0 terminates).
@@ -110,7 +121,7 @@ int pflare_b200_set_poly(void *handle, int our_level, int which, int inverse_typ
 
 /* Build the device layout: nested CF ordering, fused-operator splitting (R -> Z, P -> W),
  * ghost exchange plans, the kernel program and its CUDA graph.  Collective. */
-int pflare_b200_finalize_setup(void *handle);
+int pflare_b200_finalize_setup(void *handle);  /* collective over the ranks */
 
 /* One AIRG V-cycle: x = PCApply(b).  b, x have n_local(level 1) entries in PETSc's natural
  * local ordering.  on_device != 0: b and x are device pointers and the call is asynchronous on
@@ -136,12 +147,26 @@ int pflare_b200_synchronize(void *handle);
 int pflare_b200_get_is(void *handle, int our_level, int which_is, int *out);
 int pflare_b200_get_garray(void *handle, int our_level, int which, int64_t *out, int *n_ghost);
 
+/* The ghost-exchange plan built for one uploaded operator (multi-rank; which = the selectors above,
+ * R -> its Z block, P -> its W block): per peer rank how many entries this rank sends / receives,
+ * where each peer's chunk starts in this rank's ghost buffer (ghost order == garray order), and the
+ * positions (in the local vector segment the operator reads) this rank packs, peer after peer.
+ * Any output pointer may be NULL.  The operator's column maps themselves round-trip bit-exactly
+ * through pflare_b200_get_garray. */
+int pflare_b200_get_ghost_plan(void *handle, int our_level, int which, int *send_count, int *recv_count, int *recv_off,
+                               int *send_idx, int *n_send_idx);
+
+/* Multi-rank layout chosen at finalize: *l_agg = first level that was agglomerated onto rank 0
+ * (no_levels + 1 if none; option "agg_rows" = global-row threshold, the stand-in for the reference's
+ * processor agglomeration, src/AIR_MG_Setup.F90:645-907), global_rows[l-1] = global rows of level l. */
+int pflare_b200_get_layout(void *handle, int *l_agg, int64_t *global_rows, int n_levels);
+
 /* Counters for measurement (per apply): stats[0] = kernel launches (graph nodes that are
  * kernels of this library), [1] = algorithmic HBM bytes of one V-cycle under the model of
  * SURVEY.md section 8d, [2] = nnz traversed per cycle (nnzs_air_v of src/AIR_MG_Stats.F90:79-252),
  * [3] = device bytes held, [4] = ghost bytes sent per cycle by this rank, [5] = algorithmic
  * bytes of the largest single kernel, [6] = number of levels run by the single-CTA tail kernel,
- * [7] = NCCL send/recv groups per cycle. */
+ * [7] = ghost / agglomeration exchange groups per cycle. */
 int pflare_b200_get_stats(void *handle, double *stats, int nstats);
 
 /* Per-op timing of one apply with CUDA events (disables the graph for that apply).
@@ -150,13 +175,33 @@ int pflare_b200_get_stats(void *handle, double *stats, int nstats);
 int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, int max_ops, float *ms, double *bytes,
                               int *level, int *kind, int *n_ops);
 
-/* Runtime switches: key "graph" (0/1), "tail_rows" (levels with <= this many rows run in the
- * single-CTA tail kernel), "fuse" (0/1 fused epilogues vs one kernel per PETSc call). */
+/* Runtime switches: key "graph" (0/1), "tail_rows" / "tail_nnz" (levels with <= this many rows and
+ * nonzeros per operator run in the single-CTA tail kernel), "fuse" (0/1 fused epilogues vs one kernel
+ * per PETSc call), "kernel" (SpMV kernel variant; 0 = first-generation smem-staged kernel, 1.. =
+ * TMA-pipelined variants; variants other than 0 must be chosen before finalize_setup), "ctas_per_sm",
+ * "agg_rows" (multi-rank, before finalize_setup: levels with <= this many global rows are agglomerated
+ * onto rank 0; 0 = never). */
 int pflare_b200_set_option(void *handle, const char *key, double value);
 
 const char *pflare_b200_last_error(void);
 
 int pflare_b200_destroy(void **handle);
+
+/* In-process rank group: `nranks` logical ranks of a partitioned hierarchy driven by ONE process on
+ * one device and one stream, executed in lockstep; ghost exchanges are device-to-device copies.
+ * (One process per GPU uses pflare_b200_create with a unique id and NCCL instead.)  Each rank's
+ * operators are uploaded through its own handle (pflare_b200_cluster_rank + the set_* calls);
+ * finalize / apply / destroy go through the group.  b[r] / x[r] / y[r] are rank r's local rows.
+ * device == -1 gives a host-only planning group (no GPU needed; apply fails loudly). */
+int pflare_b200_cluster_create(void **cluster, int nranks, int device, int no_levels);
+int pflare_b200_cluster_rank(void *cluster, int rank, void **handle);
+int pflare_b200_cluster_finalize(void *cluster);
+int pflare_b200_cluster_apply(void *cluster, const double *const *b, double *const *x, int on_device);
+int pflare_b200_cluster_inv_apply(void *cluster, int our_level, int which, const double *const *x, double *const *y,
+                                  int on_device);
+int pflare_b200_cluster_set_option(void *cluster, const char *key, double value);
+int pflare_b200_cluster_get_stream(void *cluster, void **stream);
+int pflare_b200_cluster_destroy(void **cluster);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,17 @@ SIGNATURES = {
     "pflare_b200_set_option": (c_int, [c_vp, ctypes.c_char_p, c_dbl]),
     "pflare_b200_last_error": (ctypes.c_char_p, []),
     "pflare_b200_destroy": (c_int, [P(c_vp)]),
+    "pflare_b200_set_host_exchange": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "pflare_b200_get_ghost_plan": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, P(c_int)]),
+    "pflare_b200_get_layout": (c_int, [c_vp, P(c_int), c_vp, c_int]),
+    "pflare_b200_cluster_create": (c_int, [P(c_vp), c_int, c_int, c_int]),
+    "pflare_b200_cluster_rank": (c_int, [c_vp, c_int, P(c_vp)]),
+    "pflare_b200_cluster_finalize": (c_int, [c_vp]),
+    "pflare_b200_cluster_apply": (c_int, [c_vp, c_vp, c_vp, c_int]),
+    "pflare_b200_cluster_inv_apply": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int]),
+    "pflare_b200_cluster_set_option": (c_int, [c_vp, ctypes.c_char_p, c_dbl]),
+    "pflare_b200_cluster_get_stream": (c_int, [c_vp, P(c_vp)]),
+    "pflare_b200_cluster_destroy": (c_int, [P(c_vp)]),
 }
 
 _lib = None

@@ -3,33 +3,40 @@
 // the PFLARE source tree.
 //
 // What this file does, in order:
-//   set_*            : copy the operators the reference's setup built (host CSR, natural
-//                      numbering, exactly the objects listed in SURVEY.md section 8b "Upload hook").
+//   set_*            : copy the operators the reference's setup built (host CSR in PETSc MPIAIJ
+//                      layout, natural numbering: the objects listed in SURVEY.md section 8b).
 //   finalize_setup   : (1) nested CF ordering -- level l vector = [F_l | level l+1 vector], so
 //                      the identity blocks of R=[Z I] and P=[W;I] (src/Grid_Transfer.F90:329-461,
 //                      588-815) become no-ops and every VecISCopy gather/scatter
 //                      (src/FC_Smooth.F90:161-417) disappears; (2) R -> Z, P -> W, all operators
-//                      relabelled into that ordering and uploaded once; (3) the V-cycle is
-//                      compiled into a fixed program of fused SpMV ops
+//                      relabelled into that ordering with their ghost columns appended, uploaded
+//                      once; (3) multi-rank: ghost-exchange plans (dist.h) and agglomeration of
+//                      the coarse levels onto rank 0 (a child context running the serial path);
+//                      (4) the V-cycle is compiled into a fixed program of fused SpMV ops
 //                      (PCMG Kaskade wiring: src/AIR_MG_Setup.F90:967-1156; F/C smoothing:
 //                      src/FC_Smooth.F90:421-640; Horner: src/Gmres_Poly.F90:1418-1484; Newton:
 //                      src/Gmres_Poly_Newton.F90:763-875; Neumann: src/Neumann_Poly.F90:19-55);
-//                      (4) the program is captured in a CUDA graph; small coarse levels run in
+//                      (5) the program is captured in a CUDA graph; small coarse levels run in
 //                      one single-CTA kernel.
 //   apply            : permute in, launch the graph, permute out.
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pflare_b200.h"
 #include "kernels.cuh"
 #include "comm.h"
+#include "dist.h"
 
 using namespace pfb;
 
@@ -77,8 +84,24 @@ struct HostCSR {
   int64_t nnz() const { return (int64_t)ja.size(); }
 };
 
+// which index space an operator's ghost columns live in (decides how the OWNER translates a
+// requested index into a position of the vector segment the operator reads)
+enum { SP_F = 0,      // global F numbering of a level: position = F-local index
+       SP_VNEST = 1,  // global natural numbering of a level whose local vector is read in nested order
+       SP_VF = 2 };   // global natural numbering of a level, only F points allowed, position = F-local index
+
+struct DevPlan {
+  GhostPlan plan;
+  int space_kind = SP_F, space_level = 0;
+  std::vector<int64_t> garray;
+  bool global_any = false;  // some rank has ghosts for this operator -> every rank runs its exchange
+  int *d_send_idx = nullptr;
+  double *d_sendbuf = nullptr;
+  double *d_xg = nullptr;
+};
+
 struct DevCSR {
-  int m = 0, n = 0;
+  int m = 0, n = 0;        // n = local columns (ghost columns are numbered n, n+1, ...)
   int64_t nnz = 0;
   int64_t nx = 0;  // distinct columns referenced (byte model)
   int64_t nnz_model = -1;  // nnz counted by the reference's work model when it differs from nnz
@@ -88,7 +111,9 @@ struct DevCSR {
   int *blk = nullptr;
   int ntiles = 0;
   TileDesc *tiles = nullptr;
-  bool valid() const { return rp != nullptr; }
+  DevPlan *xp = nullptr;   // ghost exchange (multi-rank)
+  bool is_set = false;
+  bool valid() const { return is_set; }
 };
 
 struct Inv {
@@ -118,26 +143,32 @@ struct Level {
   double *bc_save = nullptr;   // copy of b_c when the level has C smooths
   int64_t off = 0;             // offset of this level's vector in the nested arrays
   std::vector<int> pos;        // natural index -> nested position (relative to off)
+  std::vector<int> fpos;       // natural index -> F-local index or -1
   int *d_pos = nullptr, *d_inv = nullptr;
   bool any_c = false;
 };
 
-enum { OPK_SPMV = 0, OPK_EW = 1 };
+enum { OPK_SPMV = 0, OPK_EW = 1, OPK_XCHG = 2, OPK_GATHER0 = 3, OPK_SCATTER0 = 4, OPK_CHILD = 5 };
 
 struct Op {
   int kind = OPK_SPMV;
   SpmvOp s{};
   EwOp e{};
+  DevPlan *xp = nullptr;        // OPK_XCHG: which plan; xsrc = the vector segment being exchanged
+  const double *xsrc = nullptr;
   int level = 0;
-  int tag = 0;  // 1 restrict, 2 coarse, 3 A_fc(+W), 4 A_ff residual, 5 inverse, 6 elementwise, 7 fused local smooth, 8 A_cf, 9 A_cc
+  int tag = 0;  // 1 restrict, 2 coarse, 3 A_fc(+W), 4 A_ff residual, 5 inverse, 6 elementwise, 7 fused local smooth, 8 A_cf, 9 A_cc, 10 exchange
   double bytes = 0, nnz = 0;
 };
+
+struct Cluster;
 
 struct Ctx {
   int rank = 0, nranks = 1, device = 0, no_levels = 0;
   std::vector<Level> L;  // 1-based
-  bool finalized = false;
+  bool finalized = false, planned = false;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   std::vector<void *> allocs;
   double dev_bytes = 0;
   // nested vectors + scratch
@@ -161,8 +192,19 @@ struct Ctx {
   int tile_kernel = 1;   // the variant the uploaded tile lists were built for
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int dbg_seq = 0;       // measurement only (wrong results): sequential instead of indexed x gathers
+  int64_t agg_rows = 262144;  // levels with <= this many GLOBAL rows are agglomerated onto rank 0 (multi-rank)
   int num_sms = 148;
-  std::unique_ptr<Comm> comm;
+  // multi-rank
+  std::unique_ptr<Comm> comm;            // NCCL (one process per GPU)
+  std::unique_ptr<HostComm> hostcomm;    // setup-time host communicator (callbacks / in-process / NCCL-staged)
+  Cluster *cluster = nullptr;            // in-process group of ranks (lockstep execution on one stream)
+  std::deque<DevPlan> plans;
+  std::vector<Ranges> rangeV, rangeF;    // per level (1-based): ownership of natural rows / of F points
+  int l_agg = 0;                         // first agglomerated level (no_levels + 1: none)
+  int n_dist = 0;                        // number of distributed levels with an F/C structure (l < min(l_agg, NL))
+  std::unique_ptr<Ctx> child;            // rank 0: serial hierarchy of the agglomerated levels
+  double *child_b = nullptr, *child_x = nullptr;  // rank 0: global natural vectors of level l_agg
+  double ghost_bytes = 0; int xchg_groups = 0;
 };
 
 template <class T>
@@ -184,8 +226,8 @@ int dev_upload(Ctx *c, T **p, const std::vector<T> &v) {
   return 0;
 }
 
-// Row-block partition: consecutive rows with <= kTile nnz and <= kMaxRowsPerBlk rows per block;
-// a row longer than kTile forms its own block.
+// Row-block partition: consecutive rows with <= tile nnz and <= maxrows rows per block;
+// a row longer than the tile forms its own block.
 std::vector<int> make_blocks(const std::vector<int> &ia, int m, int tile = kTile, int maxrows = kMaxRowsPerBlk) {
   std::vector<int> blk;
   blk.push_back(0);
@@ -213,16 +255,31 @@ int dev_upload_padded(Ctx *c, T **p, const std::vector<T> &v, size_t pad) {
   return 0;
 }
 
-int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d) {
+// Upload one device-ordered operator.  h.n = local columns; ghost columns (if any) are numbered
+// h.n .. h.n + h.n_ghost - 1 inside h.ja and described by h.garray (global ids in `space`).
+int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int space_level = 0) {
   if (h.nnz() >= (int64_t)2147483647) return fail(3, "operator has >= 2^31 nonzeros (32-bit PetscInt only)");
   d->m = h.m;
   d->n = h.n;
   d->nnz = h.nnz();
-  std::vector<unsigned char> seen((size_t)std::max(h.n, 1), 0);
+  d->is_set = true;
+  std::vector<unsigned char> seen((size_t)std::max(h.n + h.n_ghost, 1), 0);
   int64_t nx = 0;
   for (int cidx : h.ja)
     if (!seen[cidx]) { seen[cidx] = 1; ++nx; }
   d->nx = nx;
+  if (c->nranks > 1) {
+    c->plans.emplace_back();
+    DevPlan &P = c->plans.back();
+    P.plan.init(c->nranks);
+    P.space_kind = space_kind; P.space_level = space_level;
+    P.garray = h.garray;
+    P.plan.n_ghost = h.n_ghost;
+    d->xp = &P;
+  } else if (h.n_ghost > 0) {
+    return fail(2, "operator has ghost columns but the context has a single rank");
+  }
+  if (c->device < 0) return 0;  // host-only planning context
   int rc;
   if ((rc = dev_upload_padded(c, &d->rp, h.ia, 8))) return rc;
   if ((rc = dev_upload_padded(c, &d->col, h.ja, 8))) return rc;
@@ -239,20 +296,25 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d) {
   return 0;
 }
 
-// rows permuted by rowpos (new row index), columns relabelled by colpos; columns sorted per row.
-HostCSR remap(const HostCSR &A, const int *rowpos, const int *colpos, int new_n) {
+// Device-ordered copy of an MPIAIJ operator: rows permuted by rowpos (new row index), diag-block
+// columns relabelled by colpos into [0, nloc), off-diag (ghost) columns appended as nloc + g.
+// Per row: diag entries first, then ghost entries (the order MatMult_MPIAIJ sums them), each sorted.
+HostCSR remap(const HostCSR &A, const int *rowpos, const int *colpos, int nloc) {
   HostCSR B;
   B.set = true;
   B.m = A.m;
-  B.n = new_n;
+  B.n = nloc;
+  B.n_ghost = A.n_ghost;
+  B.garray = A.garray;
+  const bool og = A.n_ghost > 0;
   B.ia.assign((size_t)A.m + 1, 0);
   for (int i = 0; i < A.m; ++i) {
     int r = rowpos ? rowpos[i] : i;
-    B.ia[(size_t)r + 1] = A.ia[i + 1] - A.ia[i];
+    B.ia[(size_t)r + 1] = A.ia[i + 1] - A.ia[i] + (og ? A.oia[i + 1] - A.oia[i] : 0);
   }
   for (int i = 0; i < A.m; ++i) B.ia[i + 1] += B.ia[i];
-  B.ja.resize(A.ja.size());
-  B.a.resize(A.a.size());
+  B.ja.resize((size_t)B.ia[A.m]);
+  B.a.resize((size_t)B.ia[A.m]);
 #pragma omp parallel for schedule(dynamic, 1024)
   for (int i = 0; i < A.m; ++i) {
     int r = rowpos ? rowpos[i] : i;
@@ -267,12 +329,16 @@ HostCSR remap(const HostCSR &A, const int *rowpos, const int *colpos, int new_n)
       if (cc < prev) sorted = false;
       prev = cc;
     }
+    const int len = p1 - p0;
     if (!sorted) {
-      const int len = p1 - p0;
       std::vector<std::pair<int, double>> tmp((size_t)len);
       for (int k = 0; k < len; ++k) tmp[k] = {B.ja[o + k], B.a[o + k]};
       std::sort(tmp.begin(), tmp.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) { return x.first < y.first; });
       for (int k = 0; k < len; ++k) { B.ja[o + k] = tmp[k].first; B.a[o + k] = tmp[k].second; }
+    }
+    if (og) {
+      int q = o + len;
+      for (int p = A.oia[i]; p < A.oia[i + 1]; ++p, ++q) { B.ja[q] = nloc + A.oja[p]; B.a[q] = A.oa[p]; }
     }
   }
   return B;
@@ -287,6 +353,7 @@ std::vector<double> extract_diag(const HostCSR &A) {
 }
 
 bool is_diag_only(const HostCSR &A) {
+  if (A.n_ghost > 0 && !A.oja.empty()) return false;
   for (int i = 0; i < A.m; ++i)
     for (int p = A.ia[i]; p < A.ia[i + 1]; ++p)
       if (A.ja[p] != i) return false;
@@ -309,9 +376,16 @@ struct Builder {
     s.rp = A.rp; s.col = A.col; s.val = A.val; s.m = A.m; s.nblk = A.nblk; s.blk = A.blk;
     s.tiles = A.tiles; s.ntiles = A.ntiles; s.dbg_seq = c->dbg_seq;
     s.x = x; s.nloc = A.n; s.beta = 1.0;
+    s.xg = A.xp ? A.xp->d_xg : nullptr;
     return s;
   }
   void push_spmv(const SpmvOp &s, const DevCSR &A, int tag, int aux_reads, int w, double extra_bytes = 0) {
+    if (A.xp && A.xp->global_any) {  // ghost scatter of MatMult_MPIAIJ: pack + point-to-point exchange of s.x
+      Op x;
+      x.kind = OPK_XCHG; x.xp = A.xp; x.xsrc = s.x; x.level = level; x.tag = 10;
+      x.bytes = 8.0 * (A.xp->plan.n_ghost + A.xp->plan.n_send());
+      out->push_back(x);
+    }
     Op o;
     o.kind = OPK_SPMV; o.s = s; o.level = level; o.tag = tag;
     o.bytes = spmv_bytes(A, aux_reads, w) + extra_bytes;
@@ -329,7 +403,6 @@ struct Builder {
     out->push_back(o);
   }
 
-  // dst (=|+=) inverse * src.   mode 1 = set, 2 = add.  A/Adiag = the matrix a polynomial applies.
   int emit_inv(const Inv &I, const DevCSR &A, const double *Adiag, int n, const double *src, double *dst, int mode) {
     double **S = c->scr;
     if (I.kind == 1) {
@@ -517,6 +590,111 @@ struct Builder {
   }
 };
 
+// ------------------------------------------------------------------ in-process rank group
+// Several logical ranks driven by ONE process on ONE stream, executed in lockstep (op i of every
+// rank, then op i+1 ...).  Ghost exchanges become device-to-device copies between the ranks'
+// buffers.  It is the single-process way to run a partitioned hierarchy (and the way the
+// multi-rank path is exercised on a one-GPU box); one process per GPU uses NCCL instead.
+struct SharedComm;
+struct Cluster {
+  std::vector<std::unique_ptr<Ctx>> ranks;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  bool finalized = false;
+  std::shared_ptr<SharedComm> shared;
+};
+
+// setup-time host communicator between the threads of a Cluster (one thread per rank)
+struct SharedComm {
+  int P;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, generation = 0;
+  std::vector<const int64_t *> a_send;
+  struct V { const char *sbuf; const int64_t *scnt, *sdsp; };
+  std::vector<V> v_send;
+  explicit SharedComm(int p) : P(p), a_send(p), v_send(p) {}
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const int gen = generation;
+    if (++arrived == P) { arrived = 0; ++generation; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != generation; });
+  }
+};
+struct SharedRankComm : HostComm {
+  std::shared_ptr<SharedComm> sc;
+  int r;
+  SharedRankComm(std::shared_ptr<SharedComm> s, int rank) : sc(s), r(rank) {}
+  int rank() const override { return r; }
+  int size() const override { return sc->P; }
+  int alltoall(const int64_t *send, int64_t *recv, std::string *) override {
+    sc->a_send[r] = send;
+    sc->barrier();
+    for (int p = 0; p < sc->P; ++p) recv[p] = sc->a_send[p][r];
+    sc->barrier();
+    return 0;
+  }
+  int alltoallv(const char *sbuf, const int64_t *scnt, const int64_t *sdsp, char *rbuf, const int64_t *rcnt, const int64_t *rdsp,
+                std::string *) override {
+    sc->v_send[r] = {sbuf, scnt, sdsp};
+    sc->barrier();
+    for (int p = 0; p < sc->P; ++p) {
+      const SharedComm::V &v = sc->v_send[p];
+      if (rcnt[p] != v.scnt[r]) return 1;
+      if (rcnt[p]) memcpy(rbuf + rdsp[p], v.sbuf + v.sdsp[r], (size_t)rcnt[p]);
+    }
+    sc->barrier();
+    return 0;
+  }
+};
+
+// setup-time host communicator over NCCL (bytes staged through device buffers); used when one
+// process per GPU runs without user-supplied MPI-style callbacks
+struct NcclHostComm : HostComm {
+  Comm *comm;
+  cudaStream_t st;
+  NcclHostComm(Comm *c, cudaStream_t s) : comm(c), st(s) {}
+  int rank() const override { return comm->rank(); }
+  int size() const override { return comm->size(); }
+  int alltoall(const int64_t *send, int64_t *recv, std::string *err) override {
+    const int P = size();
+    std::vector<int64_t> cnt(P, 8), dsp(P);
+    for (int p = 0; p < P; ++p) dsp[p] = 8 * p;
+    return alltoallv((const char *)send, cnt.data(), dsp.data(), (char *)recv, cnt.data(), dsp.data(), err);
+  }
+  int alltoallv(const char *sbuf, const int64_t *scnt, const int64_t *sdsp, char *rbuf, const int64_t *rcnt, const int64_t *rdsp,
+                std::string *err) override {
+    const int P = size();
+    int64_t st_ = 0, rt_ = 0;
+    for (int p = 0; p < P; ++p) { st_ = std::max(st_, sdsp[p] + scnt[p]); rt_ = std::max(rt_, rdsp[p] + rcnt[p]); }
+    char *ds = nullptr, *dr = nullptr;
+    auto cu = [&](cudaError_t e, const char *what) {
+      if (e != cudaSuccess) { if (err) *err = std::string(what) + ": " + cudaGetErrorString(e); return 1; }
+      return 0;
+    };
+    if (cu(cudaMalloc(&ds, (size_t)std::max<int64_t>(st_, 1)), "cudaMalloc")) return 1;
+    if (cu(cudaMalloc(&dr, (size_t)std::max<int64_t>(rt_, 1)), "cudaMalloc")) return 1;
+    if (st_ && cu(cudaMemcpyAsync(ds, sbuf, (size_t)st_, cudaMemcpyHostToDevice, st), "H2D")) return 1;
+    bool ok = comm->group_start(err);
+    for (int p = 0; p < P && ok; ++p) {
+      if (p == rank()) continue;
+      if (scnt[p]) ok = comm->send(ds + sdsp[p], (size_t)scnt[p], 1, p, st, err);
+      if (ok && rcnt[p]) ok = comm->recv(dr + rdsp[p], (size_t)rcnt[p], 1, p, st, err);
+    }
+    ok = ok && comm->group_end(err);
+    if (!ok) return 1;
+    const int me = rank();
+    if (scnt[me] && cu(cudaMemcpyAsync(dr + rdsp[me], ds + sdsp[me], (size_t)scnt[me], cudaMemcpyDeviceToDevice, st), "D2D")) return 1;
+    if (rt_ && cu(cudaMemcpyAsync(rbuf, dr, (size_t)rt_, cudaMemcpyDeviceToHost, st), "D2H")) return 1;
+    if (cu(cudaStreamSynchronize(st), "sync")) return 1;
+    cudaFree(ds); cudaFree(dr);
+    return 0;
+  }
+};
+
+// ------------------------------------------------------------------ launching
 template <int NT, int TILE, int STAGES, bool ROWMAP = false, int MINB = 1>
 int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   auto kern = spmv_tma_kernel<NT, TILE, STAGES, ROWMAP, MINB>;
@@ -535,9 +713,22 @@ int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   return 0;
 }
 
+__global__ void __launch_bounds__(kThreads) pack_kernel(int n, const int *__restrict__ idx, const double *__restrict__ x, double *__restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];
+}
+
+int launch_pack(Ctx *c, const Op &o, cudaStream_t st) {
+  const int n = o.xp->plan.n_send();
+  if (n == 0) return 0;
+  int grid = std::min((n + kThreads - 1) / kThreads, c->num_sms * 8);
+  pack_kernel<<<grid, kThreads, 0, st>>>(n, o.xp->d_send_idx, o.xsrc, o.xp->d_sendbuf);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
   if (o.kind == OPK_SPMV) {
-    if (!dry && (o.s.m == 0 || o.s.nblk == 0)) return 0;
+    if (!dry && (o.s.m == 0 || o.s.ntiles == 0)) return 0;
     int rc = 0;
     const int k = c->kernel;
     switch (k) {
@@ -570,19 +761,136 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
     }
     if (rc) return rc;
     if (dry) return 0;
-  } else {
+  } else if (o.kind == OPK_EW) {
     if (dry) return 0;
     if (o.e.n == 0) return 0;
     int grid = std::min((o.e.n + kThreads - 1) / kThreads, c->num_sms * 8);
     ew_kernel<<<grid, kThreads, 0, st>>>(o.e);
+  } else {
+    return fail(7, "internal: op kind %d cannot be launched directly", o.kind);
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+bool op_is_empty(const Op &o) {
+  return (o.kind == OPK_SPMV && (o.s.m == 0 || o.s.ntiles == 0)) || (o.kind == OPK_EW && o.e.n == 0);
+}
+
+int launch_ew_now(Ctx *c, int n, const double *a, double *out, const int *gather, const int *scatter, cudaStream_t st) {
+  Op o; o.kind = OPK_EW;
+  o.e.n = n; o.e.a = a; o.e.alpha = 1.0; o.e.out = out; o.e.mode = 1; o.e.gather = gather; o.e.scatter = scatter;
+  return launch_op(c, o, st);
+}
+
+int run_program(Ctx *c, cudaStream_t st, int *nkernels);
+
+// the agglomerated coarse levels on rank 0: natural-order vectors in, natural-order vectors out
+int run_child(Ctx *c, cudaStream_t st) {
+  Ctx *ch = c->child.get();
+  if (!ch) return 0;
+  Level &L1 = ch->L[1];
+  int rc;
+  if ((rc = launch_ew_now(ch, L1.n, c->child_b, ch->bb, L1.d_inv, nullptr, st))) return rc;
+  if ((rc = run_program(ch, st, nullptr))) return rc;
+  if ((rc = launch_ew_now(ch, L1.n, ch->xb, c->child_x, L1.d_pos, nullptr, st))) return rc;
+  return 0;
+}
+
+// Execute op lists of a group of ranks in lockstep (R.size() == 1: a serial context, or one NCCL
+// rank of a multi-process run).  All lists have the same length and op kinds by construction.
+int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op> *> &progs, int begin, int end, cudaStream_t st) {
+  const int nr = (int)R.size();
+  for (int i = begin; i < end; ++i) {
+    const int kind = (*progs[0])[i].kind;
+    if (kind == OPK_SPMV || kind == OPK_EW) {
+      for (int r = 0; r < nr; ++r) {
+        const Op &o = (*progs[r])[i];
+        if (op_is_empty(o)) continue;
+        int rc = launch_op(R[r], o, st);
+        if (rc) return rc;
+      }
+    } else if (kind == OPK_XCHG) {
+      for (int r = 0; r < nr; ++r) {
+        int rc = launch_pack(R[r], (*progs[r])[i], st);
+        if (rc) return rc;
+      }
+      if (nr > 1) {  // in-process group: copy every peer's packed chunk into my ghost buffer
+        for (int r = 0; r < nr; ++r) {
+          const DevPlan *mine = (*progs[r])[i].xp;
+          for (int p = 0; p < nr; ++p) {
+            const int cnt = mine->plan.recv_count[p];
+            if (!cnt) continue;
+            const DevPlan *theirs = (*progs[p])[i].xp;
+            CUDA_TRY(cudaMemcpyAsync(mine->d_xg + mine->plan.recv_off[p], theirs->d_sendbuf + theirs->plan.send_off[r], (size_t)cnt * 8,
+                                     cudaMemcpyDeviceToDevice, st));
+          }
+        }
+      } else if (R[0]->comm) {
+        Ctx *c = R[0];
+        const DevPlan *P = (*progs[0])[i].xp;
+        std::string err;
+        bool ok = c->comm->group_start(&err);
+        for (int p = 0; p < c->nranks && ok; ++p) {
+          if (P->plan.send_count[p]) ok = c->comm->send(P->d_sendbuf + P->plan.send_off[p], (size_t)P->plan.send_count[p], 8, p, st, &err);
+          if (ok && P->plan.recv_count[p]) ok = c->comm->recv(P->d_xg + P->plan.recv_off[p], (size_t)P->plan.recv_count[p], 8, p, st, &err);
+        }
+        ok = ok && c->comm->group_end(&err);
+        if (!ok) return fail(21, "ghost exchange: %s", err.c_str());
+      } else {
+        return fail(21, "ghost exchange requested without a communicator");
+      }
+    } else if (kind == OPK_GATHER0 || kind == OPK_SCATTER0) {
+      const bool gather = kind == OPK_GATHER0;
+      if (nr > 1) {
+        Ctx *c0 = R[0];
+        for (int r = 0; r < nr; ++r) {
+          Ctx *c = R[r];
+          const Level &LB = c->L[c->l_agg];
+          if (!LB.n) continue;
+          double *piece = (gather ? c->bb : c->xb) + LB.off;
+          double *glob = (gather ? c0->child_b : c0->child_x) + c0->rangeV[c0->l_agg].start[r];
+          CUDA_TRY(cudaMemcpyAsync(gather ? glob : piece, gather ? piece : glob, (size_t)LB.n * 8, cudaMemcpyDeviceToDevice, st));
+        }
+      } else {
+        Ctx *c = R[0];
+        const Level &LB = c->L[c->l_agg];
+        double *piece = (gather ? c->bb : c->xb) + LB.off;
+        std::string err;
+        bool ok = true;
+        if (c->rank == 0) {
+          double *glob = gather ? c->child_b : c->child_x;
+          const Ranges &rg = c->rangeV[c->l_agg];
+          ok = c->comm->group_start(&err);
+          for (int p = 1; p < c->nranks && ok; ++p) {
+            const size_t cnt = (size_t)(rg.start[p + 1] - rg.start[p]);
+            if (!cnt) continue;
+            ok = gather ? c->comm->recv(glob + rg.start[p], cnt, 8, p, st, &err) : c->comm->send(glob + rg.start[p], cnt, 8, p, st, &err);
+          }
+          ok = ok && c->comm->group_end(&err);
+          if (ok && LB.n) CUDA_TRY(cudaMemcpyAsync(gather ? glob : piece, gather ? piece : glob, (size_t)LB.n * 8, cudaMemcpyDeviceToDevice, st));
+        } else if (LB.n) {
+          ok = c->comm->group_start(&err);
+          ok = ok && (gather ? c->comm->send(piece, (size_t)LB.n, 8, 0, st, &err) : c->comm->recv(piece, (size_t)LB.n, 8, 0, st, &err));
+          ok = ok && c->comm->group_end(&err);
+        }
+        if (!ok) return fail(21, "coarse-level agglomeration exchange: %s", err.c_str());
+      }
+    } else if (kind == OPK_CHILD) {
+      for (int r = 0; r < nr; ++r) {
+        int rc = run_child(R[r], st);
+        if (rc) return rc;
+      }
+    }
+  }
   return 0;
 }
 
 int run_program(Ctx *c, cudaStream_t st, int *nkernels) {
   int nk = 0;
   const int n = (int)c->prog.size();
+  std::vector<Ctx *> R{c};
+  std::vector<const std::vector<Op> *> P{&c->prog};
   for (int i = 0; i < n; ++i) {
     if (i == c->tail_begin && c->tail_end > c->tail_begin) {
       tail_kernel<<<1, kTailThreads, 0, st>>>(c->d_tail, c->tail_end - c->tail_begin);
@@ -592,8 +900,8 @@ int run_program(Ctx *c, cudaStream_t st, int *nkernels) {
       continue;
     }
     const Op &o = c->prog[i];
-    if ((o.kind == OPK_SPMV && (o.s.m == 0 || o.s.nblk == 0)) || (o.kind == OPK_EW && o.e.n == 0)) continue;
-    int rc = launch_op(c, o, st);
+    if (op_is_empty(o)) continue;
+    int rc = exec_ops(R, P, i, i + 1, st);
     if (rc) return rc;
     ++nk;
   }
@@ -623,20 +931,25 @@ int build_graph(Ctx *c) {
 int build_program(Ctx *c) {
   c->prog.clear();
   c->tail_begin = c->tail_end = -1;
+  c->tail_levels = 0;
   const int NL = c->no_levels;
   if (NL < 2) return 0;
+  const bool agg = c->l_agg <= NL;
+  const int LB = agg ? c->l_agg : NL;  // bottom level of this context's nested vectors
   Builder B{c, &c->prog};
-  // which levels go to the single-CTA tail: the longest suffix of small levels
+  // which levels go to the single-CTA tail: the longest suffix of small levels (serial contexts only)
   int ltail = NL + 1;
-  for (int l = NL; l >= 1; --l) {
-    Level &Lv = c->L[l];
-    int64_t mx = 0;
-    for (const DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.inv_ff.d, &Lv.inv_cc.d}) mx = std::max(mx, A->nnz);
-    if (Lv.n <= c->tail_rows && mx <= c->tail_nnz) ltail = l; else break;
+  if (c->nranks == 1) {
+    for (int l = NL; l >= 1; --l) {
+      Level &Lv = c->L[l];
+      int64_t mx = 0;
+      for (const DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.inv_ff.d, &Lv.inv_cc.d}) mx = std::max(mx, A->nnz);
+      if (Lv.n <= c->tail_rows && mx <= c->tail_nnz) ltail = l; else break;
+    }
   }
   c->tail_levels = (ltail <= NL) ? NL - ltail + 1 : 0;
   // down: b_{l+1} = b_c + Z b_f  (MatRestrict with R = [Z I])
-  for (int l = 1; l <= NL - 1; ++l) {
+  for (int l = 1; l <= LB - 1; ++l) {
     Level &Lv = c->L[l];
     B.level = l;
     if (l == ltail) c->tail_begin = (int)c->prog.size();
@@ -645,8 +958,14 @@ int build_program(Ctx *c) {
     s.out = c->bb + Lv.off + Lv.nf; s.out_mode = 2;
     B.push_spmv(s, Lv.Z, 1, 0, 2);
   }
-  // coarse solve: x_L = inv_A_ff(L) b_L  (mg_coarse_shell_apply, src/FC_Smooth.F90:29-49)
-  {
+  if (agg) {
+    // agglomerated coarse levels: gather b of level l_agg on rank 0, serial sub-cycle there, scatter x back
+    Op g; g.kind = OPK_GATHER0; g.level = LB; g.tag = 10; g.bytes = 8.0 * c->L[LB].n;
+    Op ch; ch.kind = OPK_CHILD; ch.level = LB; ch.tag = 2;
+    Op sc; sc.kind = OPK_SCATTER0; sc.level = LB; sc.tag = 10; sc.bytes = 8.0 * c->L[LB].n;
+    c->prog.push_back(g); c->prog.push_back(ch); c->prog.push_back(sc);
+  } else {
+    // coarse solve: x_L = inv_A_ff(L) b_L  (mg_coarse_shell_apply, src/FC_Smooth.F90:29-49)
     Level &Lv = c->L[NL];
     B.level = NL;
     if (NL == ltail) c->tail_begin = (int)c->prog.size();
@@ -654,7 +973,7 @@ int build_program(Ctx *c) {
     if (rc) return rc;
   }
   // up: x_l = P x_{l+1}; one mg_FC_point_richardson
-  for (int l = NL - 1; l >= 1; --l) {
+  for (int l = LB - 1; l >= 1; --l) {
     Level &Lv = c->L[l];
     B.level = l;
     int rc = B.emit_fc_richardson(Lv, true);
@@ -662,7 +981,7 @@ int build_program(Ctx *c) {
     if (l == ltail) c->tail_end = (int)c->prog.size();
   }
   if (ltail == NL && c->tail_begin >= 0) c->tail_end = c->tail_begin;  // coarse level alone: not worth a tail
-  if (c->tail_begin >= 0 && c->tail_end > c->tail_begin) {
+  if (c->device >= 0 && c->tail_begin >= 0 && c->tail_end > c->tail_begin) {
     std::vector<DevOp> ops;
     for (int i = c->tail_begin; i < c->tail_end; ++i) {
       DevOp d{};
@@ -675,13 +994,593 @@ int build_program(Ctx *c) {
     c->tail_begin = c->tail_end = -1;
     c->tail_levels = 0;
   }
+  c->ghost_bytes = 0; c->xchg_groups = 0;
+  for (const Op &o : c->prog)
+    if (o.kind == OPK_XCHG) { c->ghost_bytes += 8.0 * o.xp->plan.n_send(); ++c->xchg_groups; }
+    else if (o.kind == OPK_GATHER0 || o.kind == OPK_SCATTER0) { c->ghost_bytes += o.bytes; ++c->xchg_groups; }
   return 0;
 }
 
 int check_handle(void *h, Ctx **c) {
   if (!h) return fail(1, "null handle");
   *c = (Ctx *)h;
-  CUDA_TRY(cudaSetDevice((*c)->device));
+  if ((*c)->device >= 0) CUDA_TRY(cudaSetDevice((*c)->device));
+  return 0;
+}
+
+// ------------------------------------------------------------------ setup: collectives
+int allgather_blob(Ctx *c, const std::vector<char> &mine, std::vector<std::vector<char>> *all) {
+  const int P = c->nranks;
+  if (P == 1) { all->assign(1, mine); return 0; }
+  std::vector<std::vector<char>> out((size_t)P, mine);
+  std::string err;
+  if (exchange_blobs(c->hostcomm.get(), out, all, &err)) return fail(22, "setup exchange failed: %s", err.c_str());
+  return 0;
+}
+
+// merged global-column CSR of the local rows of an uploaded MPIAIJ operator (wire format of the
+// agglomeration gather)
+void serialize_global_csr(const HostCSR &A, Writer *w) {
+  w->put<int32_t>(A.set ? 1 : 0);
+  if (!A.set) return;
+  std::vector<int64_t> ia((size_t)A.m + 1, 0), ja;
+  std::vector<double> a;
+  const bool og = A.n_ghost > 0;
+  for (int i = 0; i < A.m; ++i) {
+    std::vector<std::pair<int64_t, double>> row;
+    for (int p = A.ia[i]; p < A.ia[i + 1]; ++p) row.push_back({A.cstart + A.ja[p], A.a[p]});
+    if (og)
+      for (int p = A.oia[i]; p < A.oia[i + 1]; ++p) row.push_back({A.garray[A.oja[p]], A.oa[p]});
+    std::sort(row.begin(), row.end(), [](const std::pair<int64_t, double> &x, const std::pair<int64_t, double> &y) { return x.first < y.first; });
+    for (auto &e : row) { ja.push_back(e.first); a.push_back(e.second); }
+    ia[(size_t)i + 1] = (int64_t)ja.size();
+  }
+  w->put<int64_t>(A.m);
+  w->put_vec(ia); w->put_vec(ja); w->put_vec(a);
+}
+
+struct GlobCSR { bool set = false; int64_t m = 0; std::vector<int64_t> ia, ja; std::vector<double> a; };
+bool read_global_csr(Reader *r, GlobCSR *g) {
+  g->set = r->get<int32_t>() != 0;
+  if (!g->set) return r->ok;
+  g->m = r->get<int64_t>();
+  r->get_vec(&g->ia); r->get_vec(&g->ja); r->get_vec(&g->a);
+  return r->ok;
+}
+
+void serialize_inv(const Inv &I, Writer *w) {
+  w->put<int32_t>(I.kind);
+  if (I.kind == 1) serialize_global_csr(I.h, w);
+  else if (I.kind == 2) w->put_vec(I.hdiag);
+  else if (I.kind == 3) { w->put<int32_t>(I.type); w->put<int32_t>(I.diag_scale); w->put_vec(I.re); w->put_vec(I.im); }
+}
+
+int finalize_ctx(Ctx *c);
+int set_csr_impl(Ctx *c, int our_level, int which, int m, int n_local_cols, int64_t cstart, const int *di, const int *dj,
+                 const double *da, int n_ghost, const int *oi, const int *oj, const double *oa, const int64_t *garray);
+
+// Rank 0: assemble the serial hierarchy of the agglomerated levels from every rank's rows.
+int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
+  const int P = c->nranks, NL = c->no_levels, LA = c->l_agg;
+  c->child.reset(new Ctx());
+  Ctx *ch = c->child.get();
+  ch->rank = 0; ch->nranks = 1; ch->device = c->device; ch->no_levels = NL - LA + 1;
+  ch->L.resize((size_t)ch->no_levels + 1);
+  ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
+  ch->use_graph = 0; ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz;
+  ch->kernel = c->kernel; ch->tile_kernel = c->tile_kernel; ch->ctas_per_sm = c->ctas_per_sm;
+  std::vector<Reader> rd;
+  for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
+  for (int l = LA; l <= NL; ++l) {
+    const int cl = l - LA + 1;
+    Level &Lv = ch->L[cl];
+    Lv.set = true; Lv.rstart = 0;
+    // concatenated pieces, rank order == global order
+    GlobCSR parts[9];
+    struct InvAcc { int kind = 0; GlobCSR g; std::vector<double> diag; int type = 0, ds = 0; std::vector<double> re, im; } iv[2];
+    std::vector<int> is_f, is_c, smooth;
+    int64_t n = 0;
+    for (int p = 0; p < P; ++p) {
+      Reader &r = rd[p];
+      const int64_t pn = r.get<int64_t>();
+      std::vector<int> f, cc, sm;
+      r.get_vec(&f); r.get_vec(&cc); r.get_vec(&sm);
+      const int64_t base = c->rangeV[l].start[p];
+      for (int v : f) is_f.push_back((int)(base + v));
+      for (int v : cc) is_c.push_back((int)(base + v));
+      if (p == 0) smooth = sm;
+      n += pn;
+      for (int w = 0; w < 9; ++w) {
+        GlobCSR g;
+        if (!read_global_csr(&r, &g)) return fail(23, "agglomeration: malformed operator blob from rank %d", p);
+        if (!g.set) continue;
+        GlobCSR &acc = parts[w];
+        if (!acc.set) { acc.set = true; acc.ia.assign(1, 0); }
+        const int64_t shift = acc.ia.back();
+        for (int64_t i = 1; i <= g.m; ++i) acc.ia.push_back(g.ia[(size_t)i] + shift);
+        acc.ja.insert(acc.ja.end(), g.ja.begin(), g.ja.end());
+        acc.a.insert(acc.a.end(), g.a.begin(), g.a.end());
+        acc.m += g.m;
+      }
+      for (int k = 0; k < 2; ++k) {
+        const int kind = r.get<int32_t>();
+        InvAcc &A = iv[k];
+        if (kind) A.kind = kind;
+        if (kind == 1) {
+          GlobCSR g;
+          if (!read_global_csr(&r, &g)) return fail(23, "agglomeration: malformed inverse blob from rank %d", p);
+          if (!A.g.set) { A.g.set = true; A.g.ia.assign(1, 0); }
+          const int64_t shift = A.g.ia.back();
+          for (int64_t i = 1; i <= g.m; ++i) A.g.ia.push_back(g.ia[(size_t)i] + shift);
+          A.g.ja.insert(A.g.ja.end(), g.ja.begin(), g.ja.end());
+          A.g.a.insert(A.g.a.end(), g.a.begin(), g.a.end());
+          A.g.m += g.m;
+        } else if (kind == 2) {
+          std::vector<double> d; r.get_vec(&d);
+          A.diag.insert(A.diag.end(), d.begin(), d.end());
+        } else if (kind == 3) {
+          A.type = r.get<int32_t>(); A.ds = r.get<int32_t>();
+          std::vector<double> re, im; r.get_vec(&re); r.get_vec(&im);
+          if (A.re.empty()) { A.re = re; A.im = im; }
+        }
+      }
+      if (!r.ok) return fail(23, "agglomeration: truncated blob from rank %d", p);
+    }
+    Lv.n = (int)n; Lv.nf = (int)is_f.size(); Lv.nc = (int)is_c.size();
+    Lv.is_f = is_f; Lv.is_c = is_c; Lv.smooth = smooth;
+    Lv.any_c = false;
+    for (int s : Lv.smooth) { if (s == 0) break; if (s < 0) Lv.any_c = true; }
+    auto column_count = [&](int w) -> int {
+      switch (w) {
+        case PFLARE_B200_AFF: case PFLARE_B200_ACF: case PFLARE_B200_INV_AFF: return cl == ch->no_levels ? Lv.n : Lv.nf;
+        case PFLARE_B200_AFC: case PFLARE_B200_ACC: case PFLARE_B200_P: case PFLARE_B200_INV_ACC: return Lv.nc;
+        default: return Lv.n;  // R, COARSE
+      }
+    };
+    auto give = [&](int w, const GlobCSR &g) -> int {
+      std::vector<int> ia(g.ia.begin(), g.ia.end()), ja(g.ja.begin(), g.ja.end());
+      if (ia.empty()) ia.assign(1, 0);
+      return set_csr_impl(ch, cl, w, (int)g.m, column_count(w), 0, ia.data(), ja.data(), g.a.data(), 0, nullptr, nullptr, nullptr, nullptr);
+    };
+    int rc;
+    for (int w = 0; w < 9; ++w)
+      if (parts[w].set && (rc = give(w, parts[w]))) return rc;
+    for (int k = 0; k < 2; ++k) {
+      Inv &I = k == 0 ? Lv.inv_ff : Lv.inv_cc;
+      InvAcc &A = iv[k];
+      if (A.kind == 1) { if ((rc = give(k == 0 ? PFLARE_B200_INV_AFF : PFLARE_B200_INV_ACC, A.g))) return rc; }
+      else if (A.kind == 2) { I.kind = 2; I.hdiag = A.diag; }
+      else if (A.kind == 3) { I.kind = 3; I.type = A.type; I.diag_scale = A.ds; I.re = A.re; I.im = A.im; }
+    }
+  }
+  return finalize_ctx(ch);
+}
+
+// ------------------------------------------------------------------ setup: the layout
+int finalize_ctx(Ctx *c) {
+  const int NL = c->no_levels, P = c->nranks;
+  int rc;
+  for (int l = 1; l <= NL; ++l)
+    if (!c->L[l].set) return fail(2, "level %d was never set", l);
+  c->plans.clear();
+  // sizes must chain locally: n_{l+1} == n_coarse(l)
+  for (int l = 1; l < NL; ++l)
+    if (c->L[l + 1].n != c->L[l].nc) return fail(2, "level %d has %d rows but level %d has %d C points", l + 1, c->L[l + 1].n, l, c->L[l].nc);
+
+  // ---- X1: ownership ranges of every level + the structural flags that shape the program
+  std::vector<int64_t> onept((size_t)NL + 1, 1), affdiag((size_t)NL + 1, 1);
+  for (int l = 1; l < NL; ++l) {
+    Level &Lv = c->L[l];
+    const HostCSR &Pm = Lv.H[PFLARE_B200_P], &Aff = Lv.H[PFLARE_B200_AFF];
+    if (!Pm.set || Pm.m != Lv.n) return fail(2, "level %d: prolongator missing or wrong shape", l);
+    if (!Aff.set || Aff.m != Lv.nf) return fail(2, "level %d: A_ff missing or wrong shape", l);
+    for (int j = 0; j < Lv.nf && onept[l]; ++j) {
+      const int i = Lv.is_f[j];
+      if (i < 0 || i >= Lv.n) return fail(2, "level %d: IS_fine out of range", l);
+      int cnt = Pm.ia[i + 1] - Pm.ia[i];
+      if (Pm.n_ghost > 0) cnt += Pm.oia[i + 1] - Pm.oia[i];
+      if (cnt > 1) onept[l] = 0;
+    }
+    affdiag[l] = is_diag_only(Aff) ? 1 : 0;
+  }
+  c->rangeV.assign((size_t)NL + 2, Ranges());
+  c->rangeF.assign((size_t)NL + 2, Ranges());
+  {
+    Writer w;
+    for (int l = 1; l <= NL; ++l) { w.put<int64_t>(c->L[l].n); w.put<int64_t>(c->L[l].nf); w.put<int64_t>(onept[l]); w.put<int64_t>(affdiag[l]); }
+    std::vector<std::vector<char>> all;
+    if ((rc = allgather_blob(c, w.buf, &all))) return rc;
+    std::vector<std::vector<int64_t>> cn((size_t)NL + 1, std::vector<int64_t>(P)), cf((size_t)NL + 1, std::vector<int64_t>(P));
+    for (int p = 0; p < P; ++p) {
+      Reader r(all[p]);
+      for (int l = 1; l <= NL; ++l) {
+        cn[l][p] = r.get<int64_t>(); cf[l][p] = r.get<int64_t>();
+        if (!r.get<int64_t>()) onept[l] = 0;
+        if (!r.get<int64_t>()) affdiag[l] = 0;
+      }
+      if (!r.ok) return fail(22, "setup exchange: rank %d uploaded a different number of levels", p);
+    }
+    for (int l = 1; l <= NL; ++l) { c->rangeV[l].from_counts(cn[l]); c->rangeF[l].from_counts(cf[l]); }
+    for (int l = 1; l <= NL; ++l)
+      if (c->rangeV[l].start[c->rank] != c->L[l].rstart && P > 1)
+        return fail(2, "level %d: rstart %lld does not match the ranks' row counts (%lld)", l, (long long)c->L[l].rstart, (long long)c->rangeV[l].start[c->rank]);
+  }
+
+  // ---- coarse-level agglomeration (multi-rank): levels with few global rows move to rank 0
+  c->l_agg = NL + 1;
+  if (P > 1 && NL >= 2 && c->agg_rows > 0)
+    for (int l = 2; l <= NL; ++l)
+      if (c->rangeV[l].total() <= c->agg_rows) { c->l_agg = l; break; }
+  const bool agg = c->l_agg <= NL;
+  const int LB = agg ? c->l_agg : NL;
+  if (agg) {
+    // X2: every rank ships its rows of the agglomerated levels to rank 0
+    Writer w;
+    for (int l = c->l_agg; l <= NL; ++l) {
+      Level &Lv = c->L[l];
+      w.put<int64_t>(Lv.n);
+      w.put_vec(Lv.is_f); w.put_vec(Lv.is_c); w.put_vec(Lv.smooth);
+      for (int k = 0; k < 9; ++k) serialize_global_csr(Lv.H[k], &w);
+      serialize_inv(Lv.inv_ff, &w);
+      serialize_inv(Lv.inv_cc, &w);
+    }
+    std::vector<std::vector<char>> out((size_t)P), in;
+    out[0] = std::move(w.buf);
+    std::string err;
+    if (exchange_blobs(c->hostcomm.get(), out, &in, &err)) return fail(22, "agglomeration exchange failed: %s", err.c_str());
+    if (c->rank == 0) {
+      if ((rc = build_child(c, in))) return rc;
+      const size_t N = (size_t)c->rangeV[c->l_agg].total();
+      if (c->device >= 0) {
+        if ((rc = dev_alloc(c, &c->child_b, N))) return rc;
+        if ((rc = dev_alloc(c, &c->child_x, N))) return rc;
+      }
+    }
+  }
+
+  // ---- (1) nested positions of the distributed levels, bottom level (LB) stays in natural order
+  c->maxn = 0;
+  for (int l = LB; l >= 1; --l) {
+    Level &Lv = c->L[l];
+    Lv.pos.resize((size_t)Lv.n);
+    Lv.fpos.assign((size_t)Lv.n, -1);
+    if (l == LB) {
+      std::iota(Lv.pos.begin(), Lv.pos.end(), 0);
+    } else {
+      std::vector<unsigned char> mark((size_t)Lv.n, 0);
+      for (int j = 0; j < Lv.nf; ++j) {
+        int i = Lv.is_f[j];
+        if (i < 0 || i >= Lv.n || mark[i]) return fail(2, "level %d: IS_fine is not a valid index set", l);
+        mark[i] = 1; Lv.pos[i] = j; Lv.fpos[i] = j;
+      }
+      const std::vector<int> &pc = c->L[l + 1].pos;
+      for (int k = 0; k < Lv.nc; ++k) {
+        int i = Lv.is_c[k];
+        if (i < 0 || i >= Lv.n || mark[i]) return fail(2, "level %d: IS_coarse overlaps IS_fine or is out of range", l);
+        mark[i] = 1; Lv.pos[i] = Lv.nf + pc[k];
+      }
+    }
+    c->maxn = std::max(c->maxn, Lv.n);
+  }
+  c->L[1].off = 0;
+  for (int l = 1; l < LB; ++l) c->L[l + 1].off = c->L[l].off + c->L[l].nf;
+
+  // ---- (2) operators of the distributed levels
+  for (int l = 1; l <= LB; ++l) {
+    Level &Lv = c->L[l];
+    if (l < LB) {
+      const std::vector<int> &pc = c->L[l + 1].pos;  // local coarse index -> nested position on level l+1
+      const std::vector<int> &fpos = Lv.fpos;
+      // R = [Z I] -> Z with rows in level l+1 nested order, columns F-local (+ ghost F points of other ranks)
+      const HostCSR &R = Lv.H[PFLARE_B200_R];
+      if (!R.set || R.m != Lv.nc || R.n != Lv.n) return fail(2, "level %d: restrictor missing or wrong shape", l);
+      {
+        HostCSR Zn; Zn.set = true; Zn.m = Lv.nc; Zn.n = Lv.nf; Zn.ia.assign((size_t)Lv.nc + 1, 0);
+        for (int i = 0; i < Lv.nc; ++i) {
+          bool ident = false;
+          for (int p = R.ia[i]; p < R.ia[i + 1]; ++p) {
+            int col = R.ja[p];
+            if (fpos[col] >= 0) { Zn.ja.push_back(fpos[col]); Zn.a.push_back(R.a[p]); }
+            else if (col == Lv.is_c[i] && R.a[p] == 1.0 && !ident) ident = true;
+            else return fail(5, "level %d: restrictor row %d is not of the form [Z I]", l, i);
+          }
+          if (!ident) return fail(5, "level %d: restrictor row %d has no identity entry", l, i);
+          Zn.ia[(size_t)i + 1] = (int)Zn.ja.size();
+        }
+        Zn.n_ghost = R.n_ghost; Zn.oia = R.oia; Zn.oja = R.oja; Zn.oa = R.oa; Zn.garray = R.garray;
+        HostCSR Z = remap(Zn, pc.data(), nullptr, Lv.nf);
+        if ((rc = upload_csr(c, Z, &Lv.Z, SP_VF, l))) return rc;
+      }
+      // P = [W; I] -> W with F-local rows, columns in level l+1 nested order
+      const HostCSR &Pm = Lv.H[PFLARE_B200_P];
+      if (Pm.n != Lv.nc) return fail(2, "level %d: prolongator has the wrong number of local columns", l);
+      for (int k = 0; k < Lv.nc; ++k) {
+        int i = Lv.is_c[k];
+        const bool extra = Pm.n_ghost > 0 && Pm.oia[i + 1] > Pm.oia[i];
+        if (extra || Pm.ia[i + 1] - Pm.ia[i] != 1 || Pm.ja[Pm.ia[i]] != k || Pm.a[Pm.ia[i]] != 1.0)
+          return fail(5, "level %d: prolongator C row %d is not an identity row", l, k);
+      }
+      HostCSR Wn; Wn.set = true; Wn.m = Lv.nf; Wn.n = Lv.nc; Wn.ia.assign((size_t)Lv.nf + 1, 0);
+      const bool pg = Pm.n_ghost > 0;
+      if (pg) { Wn.n_ghost = Pm.n_ghost; Wn.garray = Pm.garray; Wn.oia.assign((size_t)Lv.nf + 1, 0); }
+      for (int j = 0; j < Lv.nf; ++j) {
+        const int i = Lv.is_f[j];
+        for (int p = Pm.ia[i]; p < Pm.ia[i + 1]; ++p) { Wn.ja.push_back(Pm.ja[p]); Wn.a.push_back(Pm.a[p]); }
+        Wn.ia[(size_t)j + 1] = (int)Wn.ja.size();
+        if (pg) {
+          for (int p = Pm.oia[i]; p < Pm.oia[i + 1]; ++p) { Wn.oja.push_back(Pm.oja[p]); Wn.oa.push_back(Pm.oa[p]); }
+          Wn.oia[(size_t)j + 1] = (int)Wn.oja.size();
+        }
+      }
+      HostCSR W = remap(Wn, nullptr, pc.data(), Lv.nc);
+      if ((rc = upload_csr(c, W, &Lv.W, SP_VNEST, l + 1))) return rc;
+      Lv.w_onepoint = onept[l] != 0;
+      // A_fc, A_ff
+      const HostCSR &Afc = Lv.H[PFLARE_B200_AFC], &Aff = Lv.H[PFLARE_B200_AFF];
+      if (!Afc.set || Afc.m != Lv.nf || Afc.n != Lv.nc) return fail(2, "level %d: A_fc missing or wrong shape", l);
+      if (Aff.n != Lv.nf) return fail(2, "level %d: A_ff has the wrong number of local columns", l);
+      HostCSR Afc2 = remap(Afc, nullptr, pc.data(), Lv.nc);
+      if ((rc = upload_csr(c, Afc2, &Lv.Afc, SP_VNEST, l + 1))) return rc;
+      if (Lv.w_onepoint) {
+        // merged A_fc|W: every row gets its W entry (or an explicit 0.0 * x_c[0]) appended as LAST entry;
+        // the ghost columns of the two operators are merged into one sorted list
+        HostCSR M; M.set = true; M.m = Lv.nf; M.n = Lv.nc; M.ia.assign((size_t)Lv.nf + 1, 0);
+        std::vector<int64_t> &ug = M.garray;
+        ug.resize(Afc2.garray.size() + W.garray.size());
+        ug.resize((size_t)(std::set_union(Afc2.garray.begin(), Afc2.garray.end(), W.garray.begin(), W.garray.end(), ug.begin()) - ug.begin()));
+        M.n_ghost = (int)ug.size();
+        auto ghost_map = [&](const std::vector<int64_t> &g) {
+          std::vector<int> mp(g.size());
+          for (size_t k = 0; k < g.size(); ++k) mp[k] = (int)(std::lower_bound(ug.begin(), ug.end(), g[k]) - ug.begin());
+          return mp;
+        };
+        const std::vector<int> ma = ghost_map(Afc2.garray), mw = ghost_map(W.garray);
+        for (int j = 0; j < Lv.nf; ++j) M.ia[j + 1] = M.ia[j] + (Afc2.ia[j + 1] - Afc2.ia[j]) + 1;
+        M.ja.resize((size_t)M.ia[Lv.nf]); M.a.resize((size_t)M.ia[Lv.nf]);
+        for (int j = 0; j < Lv.nf; ++j) {
+          int o = M.ia[j];
+          for (int p = Afc2.ia[j]; p < Afc2.ia[j + 1]; ++p) {
+            const int cc = Afc2.ja[p];
+            M.ja[o] = cc < Lv.nc ? cc : Lv.nc + ma[cc - Lv.nc]; M.a[o] = Afc2.a[p]; ++o;
+          }
+          if (W.ia[j + 1] > W.ia[j]) {
+            const int cc = W.ja[W.ia[j]];
+            M.ja[o] = cc < Lv.nc ? cc : Lv.nc + mw[cc - Lv.nc]; M.a[o] = W.a[W.ia[j]];
+          } else { M.ja[o] = 0; M.a[o] = 0.0; }
+        }
+        if (Lv.nc == 0 && M.n_ghost == 0)   // no column to point the padding entry at
+          for (size_t k = 0; k < M.ja.size(); ++k) M.ja[k] = 0;
+        if ((rc = upload_csr(c, M, &Lv.Afcw, SP_VNEST, l + 1))) return rc;
+        Lv.Afcw.nnz_model = Afc2.nnz() + W.nnz();
+      }
+      {
+        HostCSR Aff2 = remap(Aff, nullptr, nullptr, Lv.nf);
+        if ((rc = upload_csr(c, Aff2, &Lv.Aff, SP_F, l))) return rc;
+      }
+      Lv.aff_diag_only = affdiag[l] != 0;
+      if (c->device >= 0 && (rc = dev_upload(c, &Lv.aff_diag, extract_diag(Aff)))) return rc;
+      // inverse of A_ff
+      Inv &I = Lv.inv_ff;
+      if (I.kind == 1) {
+        if (I.h.m != Lv.nf || I.h.n != Lv.nf) return fail(2, "level %d: inv_A_ff has the wrong shape", l);
+        HostCSR M2 = remap(I.h, nullptr, nullptr, Lv.nf);
+        if ((rc = upload_csr(c, M2, &I.d, SP_F, l))) return rc;
+      } else if (I.kind == 2) {
+        if ((int)I.hdiag.size() != Lv.nf) return fail(2, "level %d: diagonal inv_A_ff has the wrong size", l);
+        if (c->device >= 0 && (rc = dev_upload(c, &I.ddiag, I.hdiag))) return rc;
+      } else if (I.kind == 0) {
+        return fail(2, "level %d: inv_A_ff not set", l);
+      }
+      // C-point smoothing operators
+      if (Lv.any_c) {
+        const HostCSR &Acf = Lv.H[PFLARE_B200_ACF], &Acc = Lv.H[PFLARE_B200_ACC];
+        if (!Acf.set || !Acc.set) return fail(2, "level %d: C smoothing requested but A_cf / A_cc not set", l);
+        HostCSR Acf2 = remap(Acf, pc.data(), nullptr, Lv.nf);
+        HostCSR Acc2 = remap(Acc, pc.data(), pc.data(), Lv.nc);
+        if ((rc = upload_csr(c, Acf2, &Lv.Acf, SP_F, l))) return rc;
+        if ((rc = upload_csr(c, Acc2, &Lv.Acc, SP_VNEST, l + 1))) return rc;
+        if (c->device >= 0 && (rc = dev_upload(c, &Lv.acc_diag, extract_diag(Acc2)))) return rc;
+        Inv &J = Lv.inv_cc;
+        if (J.kind == 1) {
+          HostCSR M2 = remap(J.h, pc.data(), pc.data(), Lv.nc);
+          if ((rc = upload_csr(c, M2, &J.d, SP_VNEST, l + 1))) return rc;
+        } else if (J.kind == 2) {
+          std::vector<double> d2((size_t)Lv.nc);
+          for (int k = 0; k < Lv.nc; ++k) d2[pc[k]] = J.hdiag[k];
+          if (c->device >= 0 && (rc = dev_upload(c, &J.ddiag, d2))) return rc;
+        } else if (J.kind == 0) {
+          return fail(2, "level %d: inv_A_cc not set", l);
+        }
+        if (c->device >= 0 && (rc = dev_alloc(c, &Lv.bc_save, (size_t)Lv.nc))) return rc;
+      }
+    } else if (!agg) {
+      // coarsest level: inv_A_ff(no_levels) (+ coarse_matrix for a matrix-free polynomial)
+      Inv &I = Lv.inv_ff;
+      const HostCSR &Cm = Lv.H[PFLARE_B200_COARSE];
+      if (Cm.set) {
+        HostCSR C2 = remap(Cm, nullptr, nullptr, Lv.n);
+        if ((rc = upload_csr(c, C2, &Lv.Coarse, SP_VNEST, l))) return rc;
+        if (c->device >= 0 && (rc = dev_upload(c, &Lv.coarse_diag, extract_diag(Cm)))) return rc;
+      }
+      if (I.kind == 1) {
+        if (I.h.m != Lv.n) return fail(2, "coarse inverse has the wrong shape");
+        HostCSR M2 = remap(I.h, nullptr, nullptr, Lv.n);
+        if ((rc = upload_csr(c, M2, &I.d, SP_VNEST, l))) return rc;
+      } else if (I.kind == 2) {
+        if ((int)I.hdiag.size() != Lv.n) return fail(2, "diagonal coarse inverse has the wrong size");
+        if (c->device >= 0 && (rc = dev_upload(c, &I.ddiag, I.hdiag))) return rc;
+      } else if (I.kind == 3) {
+        if (!Cm.set) return fail(2, "matrix-free coarse inverse needs coarse_matrix (PFLARE_B200_COARSE)");
+      } else {
+        return fail(2, "coarse inverse (inv_A_ff on the coarsest level) not set");
+      }
+    }
+  }
+
+  // ---- X3: ghost exchange plans (multi-rank): who needs which entries of whose vector segments
+  if (P > 1) {
+    std::vector<std::vector<char>> out((size_t)P), in;
+    const int nplans = (int)c->plans.size();
+    for (int p = 0; p < P; ++p) {
+      Writer w;
+      w.put<int32_t>(nplans);
+      for (DevPlan &D : c->plans) w.put<int8_t>(D.plan.n_ghost > 0 ? 1 : 0);
+      out[p] = std::move(w.buf);
+    }
+    std::string err;
+    int id = 0;
+    for (DevPlan &D : c->plans) {
+      const Ranges &sp = D.space_kind == SP_F ? c->rangeF[D.space_level] : c->rangeV[D.space_level];
+      if (plan_requests(id, D.garray, sp, c->rank, &D.plan, &out, &err)) return fail(24, "ghost plan of operator %d: %s", id, err.c_str());
+      ++id;
+    }
+    if (exchange_blobs(c->hostcomm.get(), out, &in, &err)) return fail(22, "ghost plan exchange failed: %s", err.c_str());
+    for (int q = 0; q < P; ++q) {
+      Reader r(in[q]);
+      if (r.get<int32_t>() != nplans) return fail(24, "rank %d uploaded a different set of operators", q);
+      for (DevPlan &D : c->plans)
+        if (r.get<int8_t>()) D.global_any = true;
+      while (r.ok && !r.done()) {
+        const int op = r.get<int32_t>(), cnt = r.get<int32_t>();
+        if (!r.ok || op < 0 || op >= nplans || cnt < 0) return fail(24, "malformed ghost request from rank %d", q);
+        DevPlan &D = c->plans[(size_t)op];
+        D.plan.send_off[q] = D.plan.n_send();
+        D.plan.send_count[q] = cnt;
+        const Level &Ls = c->L[D.space_level];
+        for (int k = 0; k < cnt; ++k) {
+          const int idx = r.get<int32_t>();
+          int posn = -1;
+          if (D.space_kind == SP_F) { if (idx >= 0 && idx < Ls.nf) posn = idx; }
+          else if (idx >= 0 && idx < Ls.n) posn = D.space_kind == SP_VNEST ? Ls.pos[idx] : Ls.fpos[idx];
+          if (posn < 0) return fail(24, "rank %d requested an entry this rank cannot serve (operator %d)", q, op);
+          D.plan.send_idx.push_back(posn);
+        }
+      }
+      if (!r.ok) return fail(24, "truncated ghost request from rank %d", q);
+    }
+    if (c->device >= 0)
+      for (DevPlan &D : c->plans) {
+        if ((rc = dev_upload(c, &D.d_send_idx, D.plan.send_idx))) return rc;
+        if ((rc = dev_alloc(c, &D.d_sendbuf, (size_t)D.plan.n_send()))) return rc;
+        if ((rc = dev_alloc(c, &D.d_xg, (size_t)D.plan.n_ghost))) return rc;
+      }
+  }
+  c->planned = true;
+  if (c->device < 0) {  // host-only planning context: the program is still built (op list, counters), nothing runs
+    if ((rc = build_program(c))) return rc;
+    return 0;
+  }
+
+  // ---- (3) vectors
+  const size_t n1 = (size_t)c->L[1].n;
+  if ((rc = dev_alloc(c, &c->xb, n1 + 8))) return rc;   // + padding: the A_fc|W padding entry may point one past an empty C block
+  if ((rc = dev_alloc(c, &c->bb, n1 + 8))) return rc;
+  for (int k = 0; k < 7; ++k)
+    if ((rc = dev_alloc(c, &c->scr[k], (size_t)c->maxn))) return rc;
+  if ((rc = dev_alloc(c, &c->io_b, (size_t)c->maxn))) return rc;
+  if ((rc = dev_alloc(c, &c->io_x, (size_t)c->maxn))) return rc;
+  CUDA_TRY(cudaMemset(c->xb, 0, (n1 + 8) * 8));
+  CUDA_TRY(cudaMemset(c->bb, 0, (n1 + 8) * 8));
+  {
+    Level &L1 = c->L[1];
+    std::vector<int> inv((size_t)L1.n);
+    for (int i = 0; i < L1.n; ++i) inv[L1.pos[i]] = i;
+    if ((rc = dev_upload(c, &L1.d_pos, L1.pos))) return rc;
+    if ((rc = dev_upload(c, &L1.d_inv, inv))) return rc;
+  }
+  // ---- (4) program + graph
+  if ((rc = build_program(c))) return rc;
+  if (c->use_graph && NL >= 2 && !c->cluster) {
+    if ((rc = build_graph(c))) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->finalized = true;
+  return 0;
+}
+
+int ensure_level_perm(Ctx *c, Level &Lv) {
+  if (Lv.d_pos) return 0;
+  std::vector<int> inv((size_t)Lv.n);
+  for (int i = 0; i < Lv.n; ++i) inv[Lv.pos[i]] = i;
+  int rc;
+  if ((rc = dev_upload(c, &Lv.d_pos, Lv.pos))) return rc;
+  if ((rc = dev_upload(c, &Lv.d_inv, inv))) return rc;
+  return 0;
+}
+
+int set_csr_impl(Ctx *c, int our_level, int which, int m, int n_local_cols, int64_t cstart, const int *di, const int *dj,
+                 const double *da, int n_ghost, const int *oi, const int *oj, const double *oa, const int64_t *garray) {
+  if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);
+  if (which < 0 || which > 8) return fail(2, "bad operator selector %d", which);
+  Level &Lv = c->L[our_level];
+  HostCSR *H = &Lv.H[which];
+  if (which == PFLARE_B200_INV_AFF) { Lv.inv_ff.kind = 1; H = &Lv.inv_ff.h; }
+  if (which == PFLARE_B200_INV_ACC) { Lv.inv_cc.kind = 1; H = &Lv.inv_cc.h; }
+  H->set = true; H->m = m; H->n = n_local_cols; H->cstart = cstart;
+  H->ia.assign(di, di + m + 1);
+  H->ja.assign(dj, dj + di[m]);
+  H->a.assign(da, da + di[m]);
+  H->n_ghost = n_ghost;
+  H->oia.clear(); H->oja.clear(); H->oa.clear(); H->garray.clear();
+  if (n_ghost > 0) {
+    H->oia.assign(oi, oi + m + 1);
+    H->oja.assign(oj, oj + oi[m]);
+    H->oa.assign(oa, oa + oi[m]);
+    H->garray.assign(garray, garray + n_ghost);
+  }
+  c->finalized = false;
+  return 0;
+}
+
+// one context's apply on the handle's stream (serial context or one NCCL rank)
+int apply_ctx(Ctx *c, const double *b, double *x, int on_device) {
+  Level &L1 = c->L[1];
+  const double *bd = b;
+  double *xd = x;
+  int rc;
+  if (!on_device) {
+    CUDA_TRY(cudaMemcpyAsync(c->io_b, b, (size_t)L1.n * 8, cudaMemcpyHostToDevice, c->stream));
+    bd = c->io_b; xd = c->io_x;
+  }
+  if ((rc = launch_ew_now(c, L1.n, bd, c->bb, L1.d_inv, nullptr, c->stream))) return rc;  // bb[p] = b[inv[p]]
+  if (c->use_graph && c->gexec) {
+    CUDA_TRY(cudaGraphLaunch(c->gexec, c->stream));
+  } else {
+    if ((rc = run_program(c, c->stream, nullptr))) return rc;
+  }
+  if ((rc = launch_ew_now(c, L1.n, c->xb, xd, L1.d_pos, nullptr, c->stream))) return rc;  // x[i] = xb[pos[i]]
+  if (!on_device) {
+    CUDA_TRY(cudaMemcpyAsync(x, c->io_x, (size_t)L1.n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+// ops of one inverse apply (PCPFLAREINV / seam 3) on a context; in/out are c->bb / c->xb
+int build_inv_ops(Ctx *c, int our_level, int which, std::vector<Op> *ops, int *n_out, const int **perm, const int **iperm) {
+  if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);
+  if (c->l_agg <= c->no_levels && our_level >= c->l_agg) return fail(2, "level %d is agglomerated on rank 0; its inverse cannot be applied on its own", our_level);
+  Level &Lv = c->L[our_level];
+  const bool coarse = our_level == c->no_levels;
+  const Inv *I; const DevCSR *A; const double *Ad; int n;
+  *perm = *iperm = nullptr;
+  int rc;
+  if (which == PFLARE_B200_INV_AFF) {
+    I = &Lv.inv_ff; A = coarse ? &Lv.Coarse : &Lv.Aff; Ad = coarse ? Lv.coarse_diag : Lv.aff_diag; n = coarse ? Lv.n : Lv.nf;
+  } else if (which == PFLARE_B200_INV_ACC) {
+    if (coarse) return fail(2, "no inv_A_cc on the coarsest level");
+    I = &Lv.inv_cc; A = &Lv.Acc; Ad = Lv.acc_diag; n = Lv.nc;
+    Level &Ln = c->L[our_level + 1];
+    if ((rc = ensure_level_perm(c, Ln))) return rc;
+    *perm = Ln.d_pos; *iperm = Ln.d_inv;
+  } else {
+    return fail(2, "inv_apply: which must be INV_AFF or INV_ACC");
+  }
+  if (I->kind == 0) return fail(4, "that inverse was not set");
+  Builder B{c, ops};
+  B.level = our_level;
+  if ((rc = B.emit_inv(*I, *A, Ad, n, c->bb, c->xb, 1))) return rc;
+  *n_out = n;
   return 0;
 }
 
@@ -698,30 +1597,49 @@ int pflare_b200_get_unique_id(void *id) {
   return 0;
 }
 
+static int create_ctx(Ctx **out, int rank, int nranks, int device, int no_levels, cudaStream_t shared_stream) {
+  if (no_levels < 1) return fail(2, "no_levels must be >= 1");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(2, "bad rank %d of %d", rank, nranks);
+  std::unique_ptr<Ctx> c(new Ctx());
+  c->rank = rank; c->nranks = nranks; c->device = device; c->no_levels = no_levels;
+  c->L.resize((size_t)no_levels + 1);
+  if (device >= 0) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      return fail(10, "no CUDA device available (%s); this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device >= ndev) return fail(10, "device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    if (shared_stream) { c->stream = shared_stream; c->own_stream = false; }
+    else CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  }
+  *out = c.release();
+  return 0;
+}
+
 int pflare_b200_create(void **handle, int rank, int nranks, const void *unique_id, int device, int no_levels) {
   if (!handle) return fail(1, "null handle pointer");
   *handle = nullptr;
-  if (no_levels < 1) return fail(2, "no_levels must be >= 1");
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0)
-    return fail(10, "no CUDA device available (%s); this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-  if (device < 0 || device >= ndev) return fail(10, "device %d out of range (%d devices)", device, ndev);
-  CUDA_TRY(cudaSetDevice(device));
-  Ctx *c = new Ctx();
-  c->rank = rank; c->nranks = nranks; c->device = device; c->no_levels = no_levels;
-  c->L.resize((size_t)no_levels + 1);
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  c->num_sms = prop.multiProcessorCount;
-  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  if (nranks > 1) {
+  Ctx *c = nullptr;
+  int rc = create_ctx(&c, rank, nranks, device, no_levels, nullptr);
+  if (rc) return rc;
+  if (nranks > 1 && device >= 0) {
     if (!unique_id) { delete c; return fail(20, "nranks > 1 needs a unique id"); }
     std::string err;
     c->comm.reset(Comm::create(rank, nranks, unique_id, &err));
     if (!c->comm) { delete c; return fail(20, "communicator: %s", err.c_str()); }
   }
   *handle = c;
+  return 0;
+}
+
+int pflare_b200_set_host_exchange(void *handle, void *alltoall_fn, void *alltoallv_fn, void *ctx) {
+  Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  if (!alltoall_fn || !alltoallv_fn) return fail(2, "set_host_exchange: null callback");
+  c->hostcomm.reset(new CallbackComm(c->rank, c->nranks, (pfb_alltoall_fn)alltoall_fn, (pfb_alltoallv_fn)alltoallv_fn, ctx));
   return 0;
 }
 
@@ -745,26 +1663,7 @@ int pflare_b200_set_csr(void *handle, int our_level, int which, int m, int n_loc
                         const int *dj, const double *da, int n_ghost, const int *oi, const int *oj, const double *oa,
                         const int64_t *garray) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
-  if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);
-  if (which < 0 || which > 8) return fail(2, "bad operator selector %d", which);
-  Level &Lv = c->L[our_level];
-  HostCSR *H = &Lv.H[which];
-  if (which == PFLARE_B200_INV_AFF) { Lv.inv_ff.kind = 1; H = &Lv.inv_ff.h; }
-  if (which == PFLARE_B200_INV_ACC) { Lv.inv_cc.kind = 1; H = &Lv.inv_cc.h; }
-  H->set = true; H->m = m; H->n = n_local_cols; H->cstart = cstart;
-  H->ia.assign(di, di + m + 1);
-  H->ja.assign(dj, dj + di[m]);
-  H->a.assign(da, da + di[m]);
-  H->n_ghost = n_ghost;
-  H->oia.clear(); H->oja.clear(); H->oa.clear(); H->garray.clear();
-  if (n_ghost > 0) {
-    H->oia.assign(oi, oi + m + 1);
-    H->oja.assign(oj, oj + oi[m]);
-    H->oa.assign(oa, oa + oi[m]);
-    H->garray.assign(garray, garray + n_ghost);
-  }
-  c->finalized = false;
-  return 0;
+  return set_csr_impl(c, our_level, which, m, n_local_cols, cstart, di, dj, da, n_ghost, oi, oj, oa, garray);
 }
 
 int pflare_b200_set_diag(void *handle, int our_level, int which, int n, const double *d) {
@@ -799,267 +1698,41 @@ int pflare_b200_set_poly(void *handle, int our_level, int which, int inverse_typ
 
 int pflare_b200_finalize_setup(void *handle) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
-  const int NL = c->no_levels;
-  if (c->nranks > 1) return fail(30, "multi-rank finalize not available in this build");
-  for (int l = 1; l <= NL; ++l)
-    if (!c->L[l].set) return fail(2, "level %d was never set", l);
-  // sizes must chain: n_{l+1} == n_coarse(l)
-  for (int l = 1; l < NL; ++l)
-    if (c->L[l + 1].n != c->L[l].nc) return fail(2, "level %d has %d rows but level %d has %d C points", l + 1, c->L[l + 1].n, l, c->L[l].nc);
-  // (1) nested positions, coarsest first
-  c->maxn = 0;
-  for (int l = NL; l >= 1; --l) {
-    Level &Lv = c->L[l];
-    Lv.pos.resize((size_t)Lv.n);
-    if (l == NL) {
-      std::iota(Lv.pos.begin(), Lv.pos.end(), 0);
-    } else {
-      std::vector<unsigned char> mark((size_t)Lv.n, 0);
-      for (int j = 0; j < Lv.nf; ++j) {
-        int i = Lv.is_f[j];
-        if (i < 0 || i >= Lv.n || mark[i]) return fail(2, "level %d: IS_fine is not a valid index set", l);
-        mark[i] = 1; Lv.pos[i] = j;
-      }
-      const std::vector<int> &pc = c->L[l + 1].pos;
-      for (int k = 0; k < Lv.nc; ++k) {
-        int i = Lv.is_c[k];
-        if (i < 0 || i >= Lv.n || mark[i]) return fail(2, "level %d: IS_coarse overlaps IS_fine or is out of range", l);
-        mark[i] = 1; Lv.pos[i] = Lv.nf + pc[k];
-      }
-    }
-    c->maxn = std::max(c->maxn, Lv.n);
+  if (c->cluster) return fail(2, "this handle belongs to an in-process rank group: call pflare_b200_cluster_finalize");
+  if (c->nranks > 1 && !c->hostcomm) {
+    if (!c->comm) return fail(20, "multi-rank setup needs NCCL (device >= 0 + unique id) or pflare_b200_set_host_exchange callbacks");
+    c->hostcomm.reset(new NcclHostComm(c->comm.get(), c->stream));
   }
-  c->L[1].off = 0;
-  for (int l = 1; l < NL; ++l) c->L[l + 1].off = c->L[l].off + c->L[l].nf;
-  // (2) operators
-  for (int l = 1; l <= NL; ++l) {
-    Level &Lv = c->L[l];
-    if (l < NL) {
-      const std::vector<int> &pc = c->L[l + 1].pos;  // coarse index -> nested position on level l+1
-      std::vector<int> fpos((size_t)Lv.n, -1);
-      for (int j = 0; j < Lv.nf; ++j) fpos[Lv.is_f[j]] = j;
-      // R = [Z I] -> Z with rows in level l+1 nested order, columns F-local
-      const HostCSR &R = Lv.H[PFLARE_B200_R];
-      if (!R.set || R.m != Lv.nc || R.n != Lv.n) return fail(2, "level %d: restrictor missing or wrong shape", l);
-      HostCSR Z; Z.set = true; Z.m = Lv.nc; Z.n = Lv.nf; Z.ia.assign((size_t)Lv.nc + 1, 0);
-      for (int i = 0; i < Lv.nc; ++i) {
-        bool ident = false; int cnt = 0;
-        for (int p = R.ia[i]; p < R.ia[i + 1]; ++p) {
-          int col = R.ja[p];
-          if (fpos[col] >= 0) ++cnt;
-          else if (col == Lv.is_c[i] && R.a[p] == 1.0 && !ident) ident = true;
-          else return fail(5, "level %d: restrictor row %d is not of the form [Z I]", l, i);
-        }
-        if (!ident) return fail(5, "level %d: restrictor row %d has no identity entry", l, i);
-        Z.ia[(size_t)pc[i] + 1] = cnt;
-      }
-      for (int i = 0; i < Lv.nc; ++i) Z.ia[i + 1] += Z.ia[i];
-      Z.ja.resize((size_t)Z.ia[Lv.nc]); Z.a.resize((size_t)Z.ia[Lv.nc]);
-      for (int i = 0; i < Lv.nc; ++i) {
-        int o = Z.ia[pc[i]];
-        for (int p = R.ia[i]; p < R.ia[i + 1]; ++p)
-          if (fpos[R.ja[p]] >= 0) { Z.ja[o] = fpos[R.ja[p]]; Z.a[o] = R.a[p]; ++o; }
-      }
-      if ((rc = upload_csr(c, Z, &Lv.Z))) return rc;
-      // P = [W; I] -> W with F-local rows, columns in level l+1 nested order
-      const HostCSR &P = Lv.H[PFLARE_B200_P];
-      if (!P.set || P.m != Lv.n || P.n != Lv.nc) return fail(2, "level %d: prolongator missing or wrong shape", l);
-      for (int k = 0; k < Lv.nc; ++k) {
-        int i = Lv.is_c[k];
-        if (P.ia[i + 1] - P.ia[i] != 1 || P.ja[P.ia[i]] != k || P.a[P.ia[i]] != 1.0)
-          return fail(5, "level %d: prolongator C row %d is not an identity row", l, k);
-      }
-      HostCSR Wn; Wn.set = true; Wn.m = Lv.nf; Wn.n = Lv.nc; Wn.ia.assign((size_t)Lv.nf + 1, 0);
-      for (int j = 0; j < Lv.nf; ++j) Wn.ia[j + 1] = Wn.ia[j] + (P.ia[Lv.is_f[j] + 1] - P.ia[Lv.is_f[j]]);
-      Wn.ja.resize((size_t)Wn.ia[Lv.nf]); Wn.a.resize((size_t)Wn.ia[Lv.nf]);
-      bool onept = true;
-      for (int j = 0; j < Lv.nf; ++j) {
-        int i = Lv.is_f[j], o = Wn.ia[j];
-        if (P.ia[i + 1] - P.ia[i] > 1) onept = false;
-        for (int p = P.ia[i]; p < P.ia[i + 1]; ++p) { Wn.ja[o] = P.ja[p]; Wn.a[o] = P.a[p]; ++o; }
-      }
-      HostCSR W = remap(Wn, nullptr, pc.data(), Lv.nc);
-      if ((rc = upload_csr(c, W, &Lv.W))) return rc;
-      Lv.w_onepoint = onept;
-      // A_fc, A_ff
-      const HostCSR &Afc = Lv.H[PFLARE_B200_AFC], &Aff = Lv.H[PFLARE_B200_AFF];
-      if (!Afc.set || Afc.m != Lv.nf || Afc.n != Lv.nc) return fail(2, "level %d: A_fc missing or wrong shape", l);
-      if (!Aff.set || Aff.m != Lv.nf || Aff.n != Lv.nf) return fail(2, "level %d: A_ff missing or wrong shape", l);
-      HostCSR Afc2 = remap(Afc, nullptr, pc.data(), Lv.nc);
-      if ((rc = upload_csr(c, Afc2, &Lv.Afc))) return rc;
-      if (onept) {
-        // merged A_fc|W: every row gets its W entry (or an explicit 0.0 * x_c[0]) appended as LAST entry
-        HostCSR M; M.set = true; M.m = Lv.nf; M.n = Lv.nc; M.ia.assign((size_t)Lv.nf + 1, 0);
-        for (int j = 0; j < Lv.nf; ++j) M.ia[j + 1] = M.ia[j] + (Afc2.ia[j + 1] - Afc2.ia[j]) + 1;
-        M.ja.resize((size_t)M.ia[Lv.nf]); M.a.resize((size_t)M.ia[Lv.nf]);
-        for (int j = 0; j < Lv.nf; ++j) {
-          int o = M.ia[j];
-          for (int p = Afc2.ia[j]; p < Afc2.ia[j + 1]; ++p) { M.ja[o] = Afc2.ja[p]; M.a[o] = Afc2.a[p]; ++o; }
-          if (W.ia[j + 1] > W.ia[j]) { M.ja[o] = W.ja[W.ia[j]]; M.a[o] = W.a[W.ia[j]]; }
-          else { M.ja[o] = 0; M.a[o] = 0.0; }
-        }
-        if ((rc = upload_csr(c, M, &Lv.Afcw))) return rc;
-        Lv.Afcw.nnz_model = Afc2.nnz() + W.nnz();
-      }
-      if ((rc = upload_csr(c, Aff, &Lv.Aff))) return rc;
-      Lv.aff_diag_only = is_diag_only(Aff);
-      if ((rc = dev_upload(c, &Lv.aff_diag, extract_diag(Aff)))) return rc;
-      // inverse of A_ff
-      Inv &I = Lv.inv_ff;
-      if (I.kind == 1) {
-        if (I.h.m != Lv.nf || I.h.n != Lv.nf) return fail(2, "level %d: inv_A_ff has the wrong shape", l);
-        if ((rc = upload_csr(c, I.h, &I.d))) return rc;
-      } else if (I.kind == 2) {
-        if ((int)I.hdiag.size() != Lv.nf) return fail(2, "level %d: diagonal inv_A_ff has the wrong size", l);
-        if ((rc = dev_upload(c, &I.ddiag, I.hdiag))) return rc;
-      } else if (I.kind == 0) {
-        return fail(2, "level %d: inv_A_ff not set", l);
-      }
-      // C-point smoothing operators
-      if (Lv.any_c) {
-        const HostCSR &Acf = Lv.H[PFLARE_B200_ACF], &Acc = Lv.H[PFLARE_B200_ACC];
-        if (!Acf.set || !Acc.set) return fail(2, "level %d: C smoothing requested but A_cf / A_cc not set", l);
-        HostCSR Acf2 = remap(Acf, pc.data(), nullptr, Lv.nf);
-        HostCSR Acc2 = remap(Acc, pc.data(), pc.data(), Lv.nc);
-        if ((rc = upload_csr(c, Acf2, &Lv.Acf))) return rc;
-        if ((rc = upload_csr(c, Acc2, &Lv.Acc))) return rc;
-        if ((rc = dev_upload(c, &Lv.acc_diag, extract_diag(Acc2)))) return rc;
-        Inv &J = Lv.inv_cc;
-        if (J.kind == 1) {
-          HostCSR M2 = remap(J.h, pc.data(), pc.data(), Lv.nc);
-          if ((rc = upload_csr(c, M2, &J.d))) return rc;
-        } else if (J.kind == 2) {
-          std::vector<double> d2((size_t)Lv.nc);
-          for (int k = 0; k < Lv.nc; ++k) d2[pc[k]] = J.hdiag[k];
-          if ((rc = dev_upload(c, &J.ddiag, d2))) return rc;
-        } else if (J.kind == 0) {
-          return fail(2, "level %d: inv_A_cc not set", l);
-        }
-        if ((rc = dev_alloc(c, &Lv.bc_save, (size_t)Lv.nc))) return rc;
-      }
-    } else {
-      // coarsest level: inv_A_ff(no_levels) (+ coarse_matrix for a matrix-free polynomial)
-      Inv &I = Lv.inv_ff;
-      const HostCSR &Cm = Lv.H[PFLARE_B200_COARSE];
-      if (Cm.set) {
-        if ((rc = upload_csr(c, Cm, &Lv.Coarse))) return rc;
-        if ((rc = dev_upload(c, &Lv.coarse_diag, extract_diag(Cm)))) return rc;
-      }
-      if (I.kind == 1) {
-        if (I.h.m != Lv.n) return fail(2, "coarse inverse has the wrong shape");
-        if ((rc = upload_csr(c, I.h, &I.d))) return rc;
-      } else if (I.kind == 2) {
-        if ((int)I.hdiag.size() != Lv.n) return fail(2, "diagonal coarse inverse has the wrong size");
-        if ((rc = dev_upload(c, &I.ddiag, I.hdiag))) return rc;
-      } else if (I.kind == 3) {
-        if (!Cm.set) return fail(2, "matrix-free coarse inverse needs coarse_matrix (PFLARE_B200_COARSE)");
-      } else {
-        return fail(2, "coarse inverse (inv_A_ff on the coarsest level) not set");
-      }
-    }
-  }
-  // (3) vectors
-  const size_t n1 = (size_t)c->L[1].n;
-  if ((rc = dev_alloc(c, &c->xb, n1))) return rc;
-  if ((rc = dev_alloc(c, &c->bb, n1))) return rc;
-  for (int k = 0; k < 7; ++k)
-    if ((rc = dev_alloc(c, &c->scr[k], (size_t)c->maxn))) return rc;
-  if ((rc = dev_alloc(c, &c->io_b, (size_t)c->maxn))) return rc;
-  if ((rc = dev_alloc(c, &c->io_x, (size_t)c->maxn))) return rc;
-  CUDA_TRY(cudaMemset(c->xb, 0, std::max<size_t>(n1, 1) * 8));
-  CUDA_TRY(cudaMemset(c->bb, 0, std::max<size_t>(n1, 1) * 8));
-  {
-    Level &L1 = c->L[1];
-    std::vector<int> inv((size_t)L1.n);
-    for (int i = 0; i < L1.n; ++i) inv[L1.pos[i]] = i;
-    if ((rc = dev_upload(c, &L1.d_pos, L1.pos))) return rc;
-    if ((rc = dev_upload(c, &L1.d_inv, inv))) return rc;
-  }
-  // (4) program + graph
-  if ((rc = build_program(c))) return rc;
-  if (c->use_graph && NL >= 2) {
-    if ((rc = build_graph(c))) return rc;
-  }
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
-  c->finalized = true;
-  return 0;
-}
-
-static int ensure_level_perm(Ctx *c, Level &Lv) {
-  if (Lv.d_pos) return 0;
-  std::vector<int> inv((size_t)Lv.n);
-  for (int i = 0; i < Lv.n; ++i) inv[Lv.pos[i]] = i;
-  int rc;
-  if ((rc = dev_upload(c, &Lv.d_pos, Lv.pos))) return rc;
-  if ((rc = dev_upload(c, &Lv.d_inv, inv))) return rc;
-  return 0;
-}
-
-static int launch_ew_now(Ctx *c, int n, const double *a, double *out, const int *gather, const int *scatter) {
-  Op o; o.kind = OPK_EW;
-  o.e.n = n; o.e.a = a; o.e.alpha = 1.0; o.e.out = out; o.e.mode = 1; o.e.gather = gather; o.e.scatter = scatter;
-  return launch_op(c, o, c->stream);
+  return finalize_ctx(c);
 }
 
 int pflare_b200_apply(void *handle, const double *b, double *x, int on_device) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  if (c->device < 0) return fail(10, "host-only planning context: no CUDA device bound, and this library has no CPU fallback");
   if (!c->finalized) return fail(6, "apply called before finalize_setup");
+  if (c->cluster) return fail(2, "this handle belongs to an in-process rank group: call pflare_b200_cluster_apply");
   if (c->no_levels < 2) return fail(6, "apply needs >= 2 levels (the reference falls back to PCJACOBI, src/AIR_MG_Setup.F90:1167-1174)");
-  Level &L1 = c->L[1];
-  const double *bd = b;
-  double *xd = x;
-  if (!on_device) {
-    CUDA_TRY(cudaMemcpyAsync(c->io_b, b, (size_t)L1.n * 8, cudaMemcpyHostToDevice, c->stream));
-    bd = c->io_b; xd = c->io_x;
-  }
-  if ((rc = launch_ew_now(c, L1.n, bd, c->bb, L1.d_inv, nullptr))) return rc;  // bb[p] = b[inv[p]]
-  if (c->use_graph && c->gexec) {
-    CUDA_TRY(cudaGraphLaunch(c->gexec, c->stream));
-  } else {
-    if ((rc = run_program(c, c->stream, nullptr))) return rc;
-  }
-  if ((rc = launch_ew_now(c, L1.n, c->xb, xd, L1.d_pos, nullptr))) return rc;  // x[i] = xb[pos[i]]
-  if (!on_device) {
-    CUDA_TRY(cudaMemcpyAsync(x, c->io_x, (size_t)L1.n * 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-  }
-  return 0;
+  return apply_ctx(c, b, x, on_device);
 }
 
 int pflare_b200_inv_apply(void *handle, int our_level, int which, const double *x, double *y, int on_device) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  if (c->device < 0) return fail(10, "host-only planning context: no CUDA device bound");
   if (!c->finalized) return fail(6, "inv_apply called before finalize_setup");
-  if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);
-  Level &Lv = c->L[our_level];
-  const bool coarse = our_level == c->no_levels;
-  const Inv *I; const DevCSR *A; const double *Ad; int n; const int *perm = nullptr, *iperm = nullptr;
-  if (which == PFLARE_B200_INV_AFF) {
-    I = &Lv.inv_ff; A = coarse ? &Lv.Coarse : &Lv.Aff; Ad = coarse ? Lv.coarse_diag : Lv.aff_diag; n = coarse ? Lv.n : Lv.nf;
-  } else if (which == PFLARE_B200_INV_ACC) {
-    if (coarse) return fail(2, "no inv_A_cc on the coarsest level");
-    I = &Lv.inv_cc; A = &Lv.Acc; Ad = Lv.acc_diag; n = Lv.nc;
-    Level &Ln = c->L[our_level + 1];
-    if ((rc = ensure_level_perm(c, Ln))) return rc;
-    perm = Ln.d_pos; iperm = Ln.d_inv;
-  } else {
-    return fail(2, "inv_apply: which must be INV_AFF or INV_ACC");
-  }
-  if (I->kind == 0) return fail(4, "that inverse was not set");
+  if (c->cluster) return fail(2, "this handle belongs to an in-process rank group: call pflare_b200_cluster_inv_apply");
+  std::vector<Op> ops;
+  int n = 0; const int *perm, *iperm;
+  if ((rc = build_inv_ops(c, our_level, which, &ops, &n, &perm, &iperm))) return rc;
   const double *xd = x; double *yd = y;
   if (!on_device) {
     CUDA_TRY(cudaMemcpyAsync(c->io_b, x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
     xd = c->io_b; yd = c->io_x;
   }
-  // work in bb (input) / xb (output) as scratch: both hold >= n entries
-  double *in = c->bb, *out = c->xb;
-  if ((rc = launch_ew_now(c, n, xd, in, iperm, nullptr))) return rc;
-  std::vector<Op> ops;
-  Builder B{c, &ops};
-  B.level = our_level;
-  if ((rc = B.emit_inv(*I, *A, Ad, n, in, out, 1))) return rc;
-  for (const Op &o : ops)
-    if ((rc = launch_op(c, o, c->stream))) return rc;
-  if ((rc = launch_ew_now(c, n, out, yd, perm, nullptr))) return rc;
+  if ((rc = launch_ew_now(c, n, xd, c->bb, iperm, nullptr, c->stream))) return rc;
+  std::vector<Ctx *> R{c};
+  std::vector<const std::vector<Op> *> Pp{&ops};
+  if ((rc = exec_ops(R, Pp, 0, (int)ops.size(), c->stream))) return rc;
+  if ((rc = launch_ew_now(c, n, c->xb, yd, perm, nullptr, c->stream))) return rc;
   if (!on_device) {
     CUDA_TRY(cudaMemcpyAsync(y, c->io_x, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1069,8 +1742,11 @@ int pflare_b200_inv_apply(void *handle, int our_level, int which, const double *
 
 int pflare_b200_fc_smooth(void *handle, int our_level, const double *b, double *x, int on_device) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  if (c->device < 0) return fail(10, "host-only planning context: no CUDA device bound");
   if (!c->finalized) return fail(6, "fc_smooth called before finalize_setup");
-  if (our_level < 1 || our_level >= c->no_levels) return fail(2, "fc_smooth: our_level %d has no smoother", our_level);
+  if (c->cluster) return fail(2, "fc_smooth is not available on an in-process rank group");
+  const int LB = c->l_agg <= c->no_levels ? c->l_agg : c->no_levels;
+  if (our_level < 1 || our_level >= LB) return fail(2, "fc_smooth: our_level %d has no smoother on this context", our_level);
   Level &Lv = c->L[our_level];
   if ((rc = ensure_level_perm(c, Lv))) return rc;
   const double *bd = b; double *xd = x;
@@ -1079,16 +1755,17 @@ int pflare_b200_fc_smooth(void *handle, int our_level, const double *b, double *
     CUDA_TRY(cudaMemcpyAsync(c->io_x, x, (size_t)Lv.n * 8, cudaMemcpyHostToDevice, c->stream));
     bd = c->io_b; xd = c->io_x;
   }
-  if ((rc = launch_ew_now(c, Lv.n, bd, c->bb + Lv.off, Lv.d_inv, nullptr))) return rc;
-  if ((rc = launch_ew_now(c, Lv.n, xd, c->xb + Lv.off, Lv.d_inv, nullptr))) return rc;
+  if ((rc = launch_ew_now(c, Lv.n, bd, c->bb + Lv.off, Lv.d_inv, nullptr, c->stream))) return rc;
+  if ((rc = launch_ew_now(c, Lv.n, xd, c->xb + Lv.off, Lv.d_inv, nullptr, c->stream))) return rc;
   std::vector<Op> ops;
   Builder B{c, &ops};
   B.level = our_level;
   if (Lv.any_c) B.push_ew(Lv.nc, c->bb + Lv.off + Lv.nf, nullptr, nullptr, 1.0, Lv.bc_save, 1);
   if ((rc = B.emit_fc_richardson(Lv, false))) return rc;
-  for (const Op &o : ops)
-    if ((rc = launch_op(c, o, c->stream))) return rc;
-  if ((rc = launch_ew_now(c, Lv.n, c->xb + Lv.off, xd, Lv.d_pos, nullptr))) return rc;
+  std::vector<Ctx *> R{c};
+  std::vector<const std::vector<Op> *> Pp{&ops};
+  if ((rc = exec_ops(R, Pp, 0, (int)ops.size(), c->stream))) return rc;
+  if ((rc = launch_ew_now(c, Lv.n, c->xb + Lv.off, xd, Lv.d_pos, nullptr, c->stream))) return rc;
   if (!on_device) {
     CUDA_TRY(cudaMemcpyAsync(x, c->io_x, (size_t)Lv.n * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1104,7 +1781,7 @@ int pflare_b200_get_stream(void *handle, void **stream) {
 
 int pflare_b200_synchronize(void *handle) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->device >= 0) CUDA_TRY(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -1128,23 +1805,73 @@ int pflare_b200_get_garray(void *handle, int our_level, int which, int64_t *out,
   return 0;
 }
 
-int pflare_b200_get_stats(void *handle, double *stats, int nstats) {
+static DevCSR *pick_dev(Ctx *c, int our_level, int which) {
+  Level &Lv = c->L[our_level];
+  switch (which) {
+    case PFLARE_B200_AFF: return &Lv.Aff;
+    case PFLARE_B200_AFC: return &Lv.Afc;
+    case PFLARE_B200_ACF: return &Lv.Acf;
+    case PFLARE_B200_ACC: return &Lv.Acc;
+    case PFLARE_B200_INV_AFF: return &Lv.inv_ff.d;
+    case PFLARE_B200_INV_ACC: return &Lv.inv_cc.d;
+    case PFLARE_B200_R: return &Lv.Z;
+    case PFLARE_B200_P: return &Lv.W;
+    case PFLARE_B200_COARSE: return &Lv.Coarse;
+  }
+  return nullptr;
+}
+
+int pflare_b200_get_ghost_plan(void *handle, int our_level, int which, int *send_count, int *recv_count, int *recv_off,
+                               int *send_idx, int *n_send_idx) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
-  double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (!c->planned) return fail(6, "get_ghost_plan called before finalize_setup");
+  if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);
+  DevCSR *A = pick_dev(c, our_level, which);
+  if (!A || !A->valid() || !A->xp) return fail(2, "operator %d of level %d has no exchange plan on this context", which, our_level);
+  const GhostPlan &P = A->xp->plan;
+  for (int p = 0; p < c->nranks; ++p) {
+    if (send_count) send_count[p] = P.send_count[p];
+    if (recv_count) recv_count[p] = P.recv_count[p];
+    if (recv_off) recv_off[p] = P.recv_off[p];
+  }
+  if (n_send_idx) *n_send_idx = P.n_send();
+  if (send_idx && P.n_send()) memcpy(send_idx, P.send_idx.data(), sizeof(int) * (size_t)P.n_send());
+  return 0;
+}
+
+int pflare_b200_get_layout(void *handle, int *l_agg, int64_t *global_rows, int n_levels) {
+  Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  if (!c->planned) return fail(6, "get_layout called before finalize_setup");
+  if (l_agg) *l_agg = c->l_agg;
+  for (int l = 1; l <= c->no_levels && l <= n_levels; ++l) global_rows[l - 1] = c->rangeV[l].total();
+  return 0;
+}
+
+static void collect_stats(Ctx *c, double *v) {
   int nk = 0;
   for (size_t i = 0; i < c->prog.size(); ++i) {
     const Op &o = c->prog[i];
-    v[1] += o.bytes; v[2] += o.nnz;
-    v[5] = std::max(v[5], o.bytes);
+    v[1] += o.kind == OPK_XCHG || o.kind == OPK_GATHER0 || o.kind == OPK_SCATTER0 ? 0.0 : o.bytes;
+    v[2] += o.nnz;
+    if (o.kind == OPK_SPMV || o.kind == OPK_EW) v[5] = std::max(v[5], o.bytes);
     const bool in_tail = (int)i >= c->tail_begin && (int)i < c->tail_end;
-    const bool empty = (o.kind == OPK_SPMV && (o.s.m == 0 || o.s.nblk == 0)) || (o.kind == OPK_EW && o.e.n == 0);
-    if (!in_tail && !empty) ++nk;
+    if (!in_tail && !op_is_empty(o) && o.kind != OPK_CHILD) ++nk;
   }
   if (c->tail_end > c->tail_begin) ++nk;
-  v[0] = nk + 2;  // + permute in / out
+  v[0] += nk;
+  v[3] += c->dev_bytes;
+  v[4] += c->ghost_bytes;
+  v[6] += c->tail_levels;
+  v[7] += c->xchg_groups;
+  if (c->child) { collect_stats(c->child.get(), v); v[0] += 2; }
+}
+
+int pflare_b200_get_stats(void *handle, double *stats, int nstats) {
+  Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  collect_stats(c, v);
+  v[0] += 2;  // + permute in / out
   v[1] += 2.0 * 20.0 * (c->no_levels >= 1 ? c->L[1].n : 0);
-  v[3] = c->dev_bytes;
-  v[6] = c->tail_levels;
   for (int i = 0; i < nstats && i < 8; ++i) stats[i] = v[i];
   return 0;
 }
@@ -1152,18 +1879,20 @@ int pflare_b200_get_stats(void *handle, double *stats, int nstats) {
 int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, int max_ops, float *ms, double *bytes,
                               int *level, int *kind, int *n_ops) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
-  if (!c->finalized || c->no_levels < 2) return fail(6, "profile_apply needs a finalized hierarchy with >= 2 levels");
+  if (!c->finalized || c->no_levels < 2 || c->cluster) return fail(6, "profile_apply needs a finalized stand-alone hierarchy with >= 2 levels");
   Level &L1 = c->L[1];
   const int n = (int)c->prog.size();
   std::vector<cudaEvent_t> ev((size_t)n + 1);
   for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
-  if ((rc = launch_ew_now(c, L1.n, b_dev, c->bb, L1.d_inv, nullptr))) return rc;
+  if ((rc = launch_ew_now(c, L1.n, b_dev, c->bb, L1.d_inv, nullptr, c->stream))) return rc;
   CUDA_TRY(cudaEventRecord(ev[0], c->stream));
+  std::vector<Ctx *> R{c};
+  std::vector<const std::vector<Op> *> Pp{&c->prog};
   for (int i = 0; i < n; ++i) {
-    if ((rc = launch_op(c, c->prog[i], c->stream))) return rc;
+    if ((rc = exec_ops(R, Pp, i, i + 1, c->stream))) return rc;
     CUDA_TRY(cudaEventRecord(ev[(size_t)i + 1], c->stream));
   }
-  if ((rc = launch_ew_now(c, L1.n, c->xb, x_dev, L1.d_pos, nullptr))) return rc;
+  if ((rc = launch_ew_now(c, L1.n, c->xb, x_dev, L1.d_pos, nullptr, c->stream))) return rc;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   int cnt = 0;
   for (int i = 0; i < n && cnt < max_ops; ++i) {
@@ -1177,13 +1906,15 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
   return 0;
 }
 
-int pflare_b200_set_option(void *handle, const char *key, double value) {
-  Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
-  std::string k(key ? key : "");
+static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   if (k == "graph") c->use_graph = value != 0;
   else if (k == "fuse") c->fuse = value != 0;
   else if (k == "tail_rows") c->tail_rows = (int)value;
   else if (k == "tail_nnz") c->tail_nnz = (int64_t)value;
+  else if (k == "agg_rows") {
+    if (c->finalized || c->planned) return fail(2, "agg_rows must be set before finalize_setup");
+    c->agg_rows = (int64_t)value;
+  }
   else if (k == "kernel") {
     const int v = (int)value;
     if (v < 0 || v >= kNumVariants) return fail(2, "kernel variant must be 0..%d", kNumVariants - 1);
@@ -1194,25 +1925,238 @@ int pflare_b200_set_option(void *handle, const char *key, double value) {
   else if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
   else if (k == "dbg_seq_gather") c->dbg_seq = (int)value;
   else return fail(2, "unknown option '%s'", k.c_str());
-  if (c->finalized) {
-    if ((rc = build_program(c))) return rc;
-    if (c->use_graph && c->no_levels >= 2) { if ((rc = build_graph(c))) return rc; }
+  if (c->child) {
+    Ctx *ch = c->child.get();
+    ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->kernel = c->kernel; ch->ctas_per_sm = c->ctas_per_sm;
+    ch->dbg_seq = c->dbg_seq;
   }
   return 0;
+}
+
+static int rebuild_after_option(Ctx *c) {
+  int rc;
+  if (c->child && c->child->finalized && (rc = build_program(c->child.get()))) return rc;
+  if (c->finalized) {
+    if ((rc = build_program(c))) return rc;
+    if (c->use_graph && c->no_levels >= 2 && !c->cluster) { if ((rc = build_graph(c))) return rc; }
+  }
+  return 0;
+}
+
+int pflare_b200_set_option(void *handle, const char *key, double value) {
+  Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  if ((rc = set_option_ctx(c, std::string(key ? key : ""), value))) return rc;
+  return rebuild_after_option(c);
+}
+
+static void destroy_ctx(Ctx *c) {
+  if (c->device >= 0) {
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->gexec) cudaGraphExecDestroy(c->gexec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    if (c->child) { destroy_ctx(c->child.release()); }
+    for (void *p : c->allocs) cudaFree(p);
+    if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
+  }
+  c->comm.reset();
+  delete c;
 }
 
 int pflare_b200_destroy(void **handle) {
   if (!handle || !*handle) return 0;
   Ctx *c = (Ctx *)*handle;
-  cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->gexec) cudaGraphExecDestroy(c->gexec);
-  if (c->graph) cudaGraphDestroy(c->graph);
-  for (void *p : c->allocs) cudaFree(p);
-  if (c->stream) cudaStreamDestroy(c->stream);
-  c->comm.reset();
-  delete c;
+  if (c->cluster) return fail(2, "this handle belongs to an in-process rank group: call pflare_b200_cluster_destroy");
+  destroy_ctx(c);
   *handle = nullptr;
+  return 0;
+}
+
+// ---------------------------------------------------------------------- in-process rank group
+int pflare_b200_cluster_create(void **cluster, int nranks, int device, int no_levels) {
+  if (!cluster) return fail(1, "null cluster pointer");
+  *cluster = nullptr;
+  if (nranks < 1) return fail(2, "nranks must be >= 1");
+  std::unique_ptr<Cluster> cl(new Cluster());
+  cl->device = device;
+  if (device >= 0) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      return fail(10, "no CUDA device available (%s); this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&cl->stream, cudaStreamNonBlocking));
+  }
+  cl->shared.reset(new SharedComm(nranks));
+  for (int r = 0; r < nranks; ++r) {
+    Ctx *c = nullptr;
+    int rc = create_ctx(&c, r, nranks, device, no_levels, cl->stream);
+    if (rc) return rc;
+    c->cluster = cl.get();
+    c->hostcomm.reset(new SharedRankComm(cl->shared, r));
+    cl->ranks.emplace_back(c);
+  }
+  *cluster = cl.release();
+  return 0;
+}
+
+int pflare_b200_cluster_rank(void *cluster, int rank, void **handle) {
+  Cluster *cl = (Cluster *)cluster;
+  if (!cl || rank < 0 || rank >= (int)cl->ranks.size()) return fail(2, "bad cluster / rank");
+  *handle = cl->ranks[(size_t)rank].get();
+  return 0;
+}
+
+static int cluster_exec(Cluster *cl, cudaStream_t st) {
+  std::vector<Ctx *> R;
+  std::vector<const std::vector<Op> *> Pp;
+  for (auto &c : cl->ranks) { R.push_back(c.get()); Pp.push_back(&c->prog); }
+  const size_t n = Pp[0]->size();
+  for (auto *p : Pp)
+    if (p->size() != n) return fail(7, "internal: rank programs differ in length");
+  return exec_ops(R, Pp, 0, (int)n, st);
+}
+
+int pflare_b200_cluster_finalize(void *cluster) {
+  Cluster *cl = (Cluster *)cluster;
+  if (!cl) return fail(1, "null cluster");
+  const int P = (int)cl->ranks.size();
+  std::vector<int> rcs((size_t)P, 0);
+  std::vector<std::string> errs((size_t)P);
+  std::vector<std::thread> th;
+  for (int r = 0; r < P; ++r)
+    th.emplace_back([&, r] {
+      Ctx *c = cl->ranks[(size_t)r].get();
+      if (c->device >= 0) cudaSetDevice(c->device);
+      rcs[(size_t)r] = finalize_ctx(c);
+      if (rcs[(size_t)r]) errs[(size_t)r] = g_err;
+    });
+  for (auto &t : th) t.join();
+  for (int r = 0; r < P; ++r)
+    if (rcs[(size_t)r]) return fail(rcs[(size_t)r], "rank %d: %s", r, errs[(size_t)r].c_str());
+  cl->finalized = true;
+  if (cl->device >= 0 && cl->ranks[0]->use_graph && cl->ranks[0]->no_levels >= 2) {
+    Ctx *c0 = cl->ranks[0].get();
+    { Op dummy; int rc0 = launch_op(c0, dummy, cl->stream, true); if (rc0) return rc0; }
+    if (cl->gexec) { cudaGraphExecDestroy(cl->gexec); cl->gexec = nullptr; }
+    if (cl->graph) { cudaGraphDestroy(cl->graph); cl->graph = nullptr; }
+    CUDA_TRY(cudaStreamBeginCapture(cl->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = cluster_exec(cl, cl->stream);
+    cudaError_t e = cudaStreamEndCapture(cl->stream, &cl->graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(100 + (int)e, "graph capture failed: %s", cudaGetErrorString(e));
+    CUDA_TRY(cudaGraphInstantiate(&cl->gexec, cl->graph, 0));
+  }
+  if (cl->device >= 0) CUDA_TRY(cudaStreamSynchronize(cl->stream));
+  return 0;
+}
+
+// b[r], x[r]: rank r's local rows (natural local ordering), host or device pointers
+int pflare_b200_cluster_apply(void *cluster, const double *const *b, double *const *x, int on_device) {
+  Cluster *cl = (Cluster *)cluster;
+  if (!cl || !cl->finalized) return fail(6, "cluster_apply called before cluster_finalize");
+  if (cl->device < 0) return fail(10, "host-only planning group: no CUDA device bound, and this library has no CPU fallback");
+  CUDA_TRY(cudaSetDevice(cl->device));
+  if (cl->ranks[0]->no_levels < 2) return fail(6, "apply needs >= 2 levels");
+  int rc;
+  cudaStream_t st = cl->stream;
+  for (size_t r = 0; r < cl->ranks.size(); ++r) {
+    Ctx *c = cl->ranks[r].get();
+    Level &L1 = c->L[1];
+    const double *bd = b[r];
+    if (!on_device) { CUDA_TRY(cudaMemcpyAsync(c->io_b, b[r], (size_t)L1.n * 8, cudaMemcpyHostToDevice, st)); bd = c->io_b; }
+    if ((rc = launch_ew_now(c, L1.n, bd, c->bb, L1.d_inv, nullptr, st))) return rc;
+  }
+  if (cl->gexec && cl->ranks[0]->use_graph) CUDA_TRY(cudaGraphLaunch(cl->gexec, st));
+  else if ((rc = cluster_exec(cl, st))) return rc;
+  for (size_t r = 0; r < cl->ranks.size(); ++r) {
+    Ctx *c = cl->ranks[r].get();
+    Level &L1 = c->L[1];
+    double *xd = on_device ? x[r] : c->io_x;
+    if ((rc = launch_ew_now(c, L1.n, c->xb, xd, L1.d_pos, nullptr, st))) return rc;
+    if (!on_device) CUDA_TRY(cudaMemcpyAsync(x[r], c->io_x, (size_t)L1.n * 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (!on_device) CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pflare_b200_cluster_inv_apply(void *cluster, int our_level, int which, const double *const *xin, double *const *y, int on_device) {
+  Cluster *cl = (Cluster *)cluster;
+  if (!cl || !cl->finalized) return fail(6, "cluster_inv_apply called before cluster_finalize");
+  if (cl->device < 0) return fail(10, "host-only planning group: no CUDA device bound");
+  CUDA_TRY(cudaSetDevice(cl->device));
+  const size_t P = cl->ranks.size();
+  std::vector<std::vector<Op>> ops(P);
+  std::vector<int> n(P, 0);
+  std::vector<const int *> perm(P), iperm(P);
+  std::vector<Ctx *> R;
+  std::vector<const std::vector<Op> *> Pp;
+  int rc;
+  cudaStream_t st = cl->stream;
+  for (size_t r = 0; r < P; ++r) {
+    Ctx *c = cl->ranks[r].get();
+    if ((rc = build_inv_ops(c, our_level, which, &ops[r], &n[r], &perm[r], &iperm[r]))) return rc;
+    R.push_back(c); Pp.push_back(&ops[r]);
+    const double *xd = xin[r];
+    if (!on_device) { CUDA_TRY(cudaMemcpyAsync(c->io_b, xin[r], (size_t)n[r] * 8, cudaMemcpyHostToDevice, st)); xd = c->io_b; }
+    if ((rc = launch_ew_now(c, n[r], xd, c->bb, iperm[r], nullptr, st))) return rc;
+  }
+  for (size_t r = 1; r < P; ++r)
+    if (ops[r].size() != ops[0].size()) return fail(7, "internal: rank op lists differ in length");
+  if ((rc = exec_ops(R, Pp, 0, (int)ops[0].size(), st))) return rc;
+  for (size_t r = 0; r < P; ++r) {
+    Ctx *c = cl->ranks[r].get();
+    double *yd = on_device ? y[r] : c->io_x;
+    if ((rc = launch_ew_now(c, n[r], c->xb, yd, perm[r], nullptr, st))) return rc;
+    if (!on_device) CUDA_TRY(cudaMemcpyAsync(y[r], c->io_x, (size_t)n[r] * 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (!on_device) CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pflare_b200_cluster_set_option(void *cluster, const char *key, double value) {
+  Cluster *cl = (Cluster *)cluster;
+  if (!cl) return fail(1, "null cluster");
+  for (auto &c : cl->ranks) {
+    int rc = set_option_ctx(c.get(), std::string(key ? key : ""), value);
+    if (rc) return rc;
+    if ((rc = rebuild_after_option(c.get()))) return rc;
+  }
+  if (cl->finalized && cl->gexec) {  // re-capture
+    cudaGraphExecDestroy(cl->gexec); cl->gexec = nullptr;
+    cudaGraphDestroy(cl->graph); cl->graph = nullptr;
+    if (cl->ranks[0]->use_graph) {
+      CUDA_TRY(cudaStreamBeginCapture(cl->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = cluster_exec(cl, cl->stream);
+      cudaError_t e = cudaStreamEndCapture(cl->stream, &cl->graph);
+      if (rc) return rc;
+      if (e != cudaSuccess) return fail(100 + (int)e, "graph capture failed: %s", cudaGetErrorString(e));
+      CUDA_TRY(cudaGraphInstantiate(&cl->gexec, cl->graph, 0));
+    }
+  }
+  return 0;
+}
+
+int pflare_b200_cluster_get_stream(void *cluster, void **stream) {
+  Cluster *cl = (Cluster *)cluster;
+  if (!cl) return fail(1, "null cluster");
+  *stream = (void *)cl->stream;
+  return 0;
+}
+
+int pflare_b200_cluster_destroy(void **cluster) {
+  if (!cluster || !*cluster) return 0;
+  Cluster *cl = (Cluster *)*cluster;
+  if (cl->device >= 0) {
+    cudaSetDevice(cl->device);
+    if (cl->stream) cudaStreamSynchronize(cl->stream);
+    if (cl->gexec) cudaGraphExecDestroy(cl->gexec);
+    if (cl->graph) cudaGraphDestroy(cl->graph);
+  }
+  for (auto &c : cl->ranks) { Ctx *p = c.release(); p->cluster = nullptr; destroy_ctx(p); }
+  if (cl->device >= 0 && cl->stream) cudaStreamDestroy(cl->stream);
+  delete cl;
+  *cluster = nullptr;
   return 0;
 }
 

@@ -33,16 +33,21 @@ def _ptr(a):
 class DeviceAIR:
     """Handle to one uploaded hierarchy (``void *handle`` of include/pflare_b200.h)."""
 
-    def __init__(self, no_levels, rank=0, nranks=1, unique_id=None, device=0):
+    def __init__(self, no_levels, rank=0, nranks=1, unique_id=None, device=0, _handle=None):
         self.L = _capi.lib()
         self.no_levels = int(no_levels)
         self.rank, self.nranks, self.device = rank, nranks, device
-        self.h = ctypes.c_void_p()
-        uid = None
-        if unique_id is not None:
-            self._uid = ctypes.create_string_buffer(bytes(unique_id), 128)
-            uid = ctypes.cast(self._uid, ctypes.c_void_p)
-        check(self.L.pflare_b200_create(ctypes.byref(self.h), rank, nranks, uid, device, self.no_levels))
+        self._owned = _handle is None
+        if _handle is not None:      # a rank of an in-process group (owned by the ClusterAIR)
+            self.h = _handle
+        else:
+            self.h = ctypes.c_void_p()
+            uid = None
+            if unique_id is not None:
+                self._uid = ctypes.create_string_buffer(bytes(unique_id), 128)
+                uid = ctypes.cast(self._uid, ctypes.c_void_p)
+            check(self.L.pflare_b200_create(ctypes.byref(self.h), rank, nranks, uid, device, self.no_levels))
+        self._cb = None
         self.n = {}
         self.nf = {}
         self.nc = {}
@@ -81,7 +86,67 @@ class DeviceAIR:
                                           int(bool(diag_scale))))
 
     def finalize(self):
-        check(self.L.pflare_b200_finalize_setup(self.h))
+        if self._owned:
+            check(self.L.pflare_b200_finalize_setup(self.h))
+        # ranks of an in-process group are finalized together by ClusterAIR.finalize()
+
+    def set_host_exchange(self, alltoall, alltoallv):
+        """Setup-time host communicator as two Python callables with MPI_Alltoall / MPI_Alltoallv semantics:
+        alltoall(send: int64[P]) -> int64[P];  alltoallv(sendbuf: bytes, scnt, sdsp, rcnt, rdsp) -> bytes."""
+        P_ = self.nranks
+        A2A = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64))
+        A2AV = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+                                ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+                                ctypes.POINTER(ctypes.c_int64))
+
+        def _a2a(ctx, send, recv):
+            try:
+                out = alltoall(np.array([send[p] for p in range(P_)], dtype=np.int64))
+                for p in range(P_):
+                    recv[p] = int(out[p])
+                return 0
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        def _a2av(ctx, sbuf, scnt, sdsp, rbuf, rcnt, rdsp):
+            try:
+                sc = [scnt[p] for p in range(P_)]
+                sd = [sdsp[p] for p in range(P_)]
+                rc_ = [rcnt[p] for p in range(P_)]
+                rd = [rdsp[p] for p in range(P_)]
+                tot = max([sd[p] + sc[p] for p in range(P_)] + [0])
+                data = ctypes.string_at(sbuf, tot) if tot else b""
+                out = alltoallv(data, sc, sd, rc_, rd)
+                if len(out):
+                    ctypes.memmove(rbuf, out, len(out))
+                return 0
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._cb = (A2A(_a2a), A2AV(_a2av))
+        check(self.L.pflare_b200_set_host_exchange(self.h, ctypes.cast(self._cb[0], ctypes.c_void_p),
+                                                   ctypes.cast(self._cb[1], ctypes.c_void_p), None))
+
+    def ghost_plan(self, our_level, which):
+        P_ = self.nranks
+        sc = np.zeros(P_, dtype=np.int32)
+        rc_ = np.zeros(P_, dtype=np.int32)
+        ro = np.zeros(P_, dtype=np.int32)
+        n = ctypes.c_int(0)
+        check(self.L.pflare_b200_get_ghost_plan(self.h, our_level, which, _ptr(sc), _ptr(rc_), _ptr(ro), None, ctypes.byref(n)))
+        idx = np.zeros(max(n.value, 1), dtype=np.int32)
+        check(self.L.pflare_b200_get_ghost_plan(self.h, our_level, which, None, None, None, _ptr(idx), ctypes.byref(n)))
+        return {"send_count": sc, "recv_count": rc_, "recv_off": ro, "send_idx": idx[:n.value]}
+
+    def layout(self):
+        la = ctypes.c_int(0)
+        rows = np.zeros(self.no_levels, dtype=np.int64)
+        check(self.L.pflare_b200_get_layout(self.h, ctypes.byref(la), _ptr(rows), self.no_levels))
+        return la.value, rows
 
     def set_option(self, key, value):
         check(self.L.pflare_b200_set_option(self.h, key.encode(), float(value)))
@@ -155,9 +220,77 @@ class DeviceAIR:
         return ms[:k], by[:k], lev[:k], kind[:k]
 
     def close(self):
-        if getattr(self, "h", None) is not None and self.h:
+        if getattr(self, "h", None) is not None and self.h and self._owned:
             self.L.pflare_b200_destroy(ctypes.byref(self.h))
-            self.h = ctypes.c_void_p()
+        self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ClusterAIR:
+    """In-process rank group (``pflare_b200_cluster_*``): a partitioned hierarchy driven by one process."""
+
+    def __init__(self, no_levels, nranks, device=0):
+        self.L = _capi.lib()
+        self.no_levels, self.nranks, self.device = int(no_levels), int(nranks), device
+        self.c = ctypes.c_void_p()
+        check(self.L.pflare_b200_cluster_create(ctypes.byref(self.c), self.nranks, device, self.no_levels))
+        self.ranks = []
+        for r in range(self.nranks):
+            h = ctypes.c_void_p()
+            check(self.L.pflare_b200_cluster_rank(self.c, r, ctypes.byref(h)))
+            self.ranks.append(DeviceAIR(no_levels, rank=r, nranks=nranks, device=device, _handle=h))
+
+    def set_option(self, key, value):
+        check(self.L.pflare_b200_cluster_set_option(self.c, key.encode(), float(value)))
+
+    def upload(self, local_hierarchies):
+        for r, lh in enumerate(local_hierarchies):
+            lh.feed(self.ranks[r])
+        self.finalize()
+        return self
+
+    def finalize(self):
+        check(self.L.pflare_b200_cluster_finalize(self.c))
+
+    def _ptr_array(self, arrs):
+        return (ctypes.c_void_p * self.nranks)(*[a.ctypes.data for a in arrs])
+
+    def apply(self, b_parts):
+        b_parts = [_f64(b) for b in b_parts]
+        x_parts = [np.empty_like(b) for b in b_parts]
+        check(self.L.pflare_b200_cluster_apply(self.c, self._ptr_array(b_parts), self._ptr_array(x_parts), 0))
+        return x_parts
+
+    def apply_ptrs(self, b_ptrs, x_ptrs, on_device=1):
+        bp = (ctypes.c_void_p * self.nranks)(*b_ptrs)
+        xp = (ctypes.c_void_p * self.nranks)(*x_ptrs)
+        check(self.L.pflare_b200_cluster_apply(self.c, bp, xp, on_device))
+
+    def inv_apply(self, our_level, which, x_parts):
+        x_parts = [_f64(x) for x in x_parts]
+        y_parts = [np.empty_like(x) for x in x_parts]
+        check(self.L.pflare_b200_cluster_inv_apply(self.c, our_level, which, self._ptr_array(x_parts), self._ptr_array(y_parts), 0))
+        return y_parts
+
+    def stream_ptr(self):
+        s = ctypes.c_void_p()
+        check(self.L.pflare_b200_cluster_get_stream(self.c, ctypes.byref(s)))
+        return s.value or 0
+
+    def stats(self):
+        return [r.stats() for r in self.ranks]
+
+    def close(self):
+        if getattr(self, "c", None) is not None and self.c:
+            for r in self.ranks:
+                r.h = ctypes.c_void_p()
+            self.L.pflare_b200_cluster_destroy(ctypes.byref(self.c))
+            self.c = ctypes.c_void_p()
 
     def __del__(self):
         try:

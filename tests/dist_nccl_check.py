@@ -1,0 +1,56 @@
+"""torchrun worker: one process per GPU, NCCL ghost exchange; every rank checks its rows of the
+distributed V-cycle against the serial oracle.  Prints NCCL_DIST_OK on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cases  # noqa: E402
+import hiergen  # noqa: E402
+import oracle  # noqa: E402
+import pflare_b200  # noqa: E402
+from pflare_b200 import _capi  # noqa: E402
+import ctypes  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    uid = [None]
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        _capi.check(_capi.lib().pflare_b200_get_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+        uid[0] = buf.raw
+    dist.broadcast_object_list(uid, src=0)
+    worst = 0.0
+    for name in ("fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "dg_mf"):
+        A, H = cases.build(name)
+        b = cases.rhs(A.shape[0])
+        xo = hiergen.feed(H, oracle.OracleAIR(H.no_levels)).apply(b)
+        parts = hiergen.partition(H, world)
+        rg = parts[0].rangesV[0]
+        for agg_rows in (0, 600):
+            pc = pflare_b200.PC(rank=rank, nranks=world, unique_id=uid[0], device=local).setType("air").setHierarchy(parts[rank])
+            pc.setOption("agg_rows", agg_rows)
+            x = pc.apply(b[rg[rank]:rg[rank + 1]])
+            err = np.linalg.norm(x - xo[rg[rank]:rg[rank + 1]]) / np.linalg.norm(xo)
+            worst = max(worst, err)
+            pc.destroy()
+    t = torch.tensor([worst], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("worst relative error %.3e" % t.item())
+        assert t.item() <= 1e-12
+        print("NCCL_DIST_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
