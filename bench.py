@@ -223,23 +223,49 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    A, H, name = build_hierarchy(args)
-    n = A.shape[0]
     if world > 1:
-        raise SystemExit("multi-GPU bench path not available yet")
-    pc = pflare_b200.PC(device=local).setType("air").setHierarchy(H)
+        # rank 0 builds (or loads) the hierarchy and caches it; the others load it from the cache
+        if rank == 0:
+            A, H, name = build_hierarchy(args)
+        dist.barrier()
+        if rank != 0:
+            A, H, name = build_hierarchy(args)
+    else:
+        A, H, name = build_hierarchy(args)
+    n = A.shape[0]
+    t = time.time()
+    if world > 1:
+        import ctypes
+        import hiergen
+        from pflare_b200 import _capi
+        uid = [None]
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            _capi.check(_capi.lib().pflare_b200_get_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+            uid[0] = buf.raw
+        dist.broadcast_object_list(uid, src=0)
+        part = hiergen.partition(H, world, only=rank)[rank]
+        rows0 = part.rangesV[0]
+        n_local = int(rows0[rank + 1] - rows0[rank])
+        log("[bench] rank %d: rows [%d, %d), partitioned in %.1f s" % (rank, rows0[rank], rows0[rank + 1], time.time() - t))
+        pc = pflare_b200.PC(rank=rank, nranks=world, unique_id=uid[0], device=local).setType("air").setHierarchy(part)
+    else:
+        n_local = n
+        pc = pflare_b200.PC(device=local).setType("air").setHierarchy(H)
     for kv in args.opt:
         k, v = kv.split("=")
         pc.setOption(k, float(v))
     t = time.time()
     pc.setUp()
     dev = pc.device()
-    log("[bench] upload + finalize: %.1f s" % (time.time() - t))
+    log("[bench] rank %d upload + finalize: %.1f s" % (rank, time.time() - t))
     st = dev.stats()
     stream = torch.cuda.ExternalStream(dev.stream_ptr(), device=torch.device("cuda", local))
 
-    b_host = torch.from_numpy(np.random.default_rng(1234).random(n)).pin_memory()
-    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    b_full = np.random.default_rng(1234).random(n)
+    lo = int(rows0[rank]) if world > 1 else 0
+    b_host = torch.from_numpy(np.ascontiguousarray(b_full[lo:lo + n_local])).pin_memory()
+    x_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
     b = b_host.cuda()
     x = torch.empty_like(b)
     torch.cuda.synchronize()
@@ -316,12 +342,19 @@ def run_gpu(args):
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
         "kernel": "spmv_stream_kernel", "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650",
         "how": "sum of algorithmic bytes of all spmv_stream_kernel launches of one V-cycle / sum of their CUDA-event durations (launch by launch, graph off)",
-        "cycle_achieved": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9,
+        "cycle_achieved": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9,      # this rank's bytes / the cycle time
         "cycle_frac": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9 / peak,
         "largest_launch": {"bytes": biggest[0], "ms": biggest[1], "level": biggest[2],
                            "GBps": biggest[0] / (biggest[1] * 1e-3) / 1e9 if biggest[1] > 0 else None},
         "algorithmic_bytes_per_cycle": st["algorithmic_bytes"], "nnz_per_cycle": st["nnz_per_cycle"],
     }
+
+    # whole-job counters (bytes / launches summed over the ranks)
+    tot = torch.tensor([st["algorithmic_bytes"], st["kernel_launches"], st["ghost_bytes_sent"], st["device_bytes"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot)
+    job_bytes, job_launches, job_ghost, job_dev = [float(v) for v in tot.tolist()]
+    l_agg, glob_rows = dev.layout() if world > 1 else (H.no_levels + 1, None)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -332,16 +365,19 @@ def run_gpu(args):
 
     if rank == 0:
         out = {
-            "metric": "AIRG V-cycle DOF/s", "value": n * world / (ms_dev * 1e-3) if False else n / (ms_dev * 1e-3),
+            "metric": "AIRG V-cycle DOF/s", "value": n / (ms_dev * 1e-3),
             "unit": "DOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "rows": n, "levels": H.no_levels, "nnz_level1": int(A.nnz),
-                       "l2": "inputs larger than L2: %.2f GB of operators streamed per cycle, no flush" % (st["algorithmic_bytes"] / 1e9),
-                       "device_bytes": st["device_bytes"], "rhs": "seeded uniform(0,1), seed 1234"},
+                       "l2": "inputs larger than L2: %.2f GB of operators streamed per cycle (whole job), no flush" % (job_bytes / 1e9),
+                       "device_bytes": job_dev, "rhs": "seeded uniform(0,1), seed 1234",
+                       "partition": "1 GPU" if world == 1 else "%d ranks, contiguous row blocks (PETSc MPIAIJ ownership), ghost exchange = NCCL send/recv, levels >= %d agglomerated on rank 0" % (world, l_agg),
+                       "ghost_bytes_per_cycle": job_ghost, "exchange_groups_per_cycle_rank0": int(st["exchange_groups"]),
+                       "library_options": args.opt},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "DOF/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
-            "gpu_launches": int(st["kernel_launches"]) * args.steps,
+                    "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n, "note": "summed over ranks"},
+            "gpu_launches": int(job_launches) * args.steps,
             "launches_per_cycle": int(st["kernel_launches"]), "tail_levels": int(st["tail_levels"]),
             "clocks": clocks,
         }
@@ -358,7 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PFLARE_BENCH_WORKLOAD", "adv_diff_fd_2d"))
-    ap.add_argument("--n", type=int, default=int(os.environ.get("PFLARE_BENCH_N", "4096")))
+    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("PFLARE_BENCH_N", "4096")))
     ap.add_argument("--cpu-cycles", type=int, default=5)
     ap.add_argument("--ref-max-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")

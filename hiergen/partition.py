@@ -79,13 +79,16 @@ class LocalHierarchy:
                     sink.set_diag(l, which, payload)
                 else:
                     sink.set_poly(l, which, payload["type"], payload["coeffs"], payload["diag_scale"])
+        sink.finalize()   # collective over the ranks (a no-op for the ranks of an in-process group)
         return sink
 
 
-def partition(H, nranks):
-    """Returns [LocalHierarchy for rank 0 .. nranks-1]."""
+def partition(H, nranks, only=None):
+    """Returns [LocalHierarchy for rank 0 .. nranks-1]; with ``only=r`` just rank r's piece is
+    materialised (the other entries carry the ownership ranges only)."""
     NL = H.no_levels
     out = [LocalHierarchy(r, nranks, NL) for r in range(nranks)]
+    todo = range(nranks) if only is None else [only]
     rv = split_ownership(H.levels[0].n if H.levels else H.coarse_matrix.shape[0], nranks)
 
     def local_inv(inv, rrange, crange, r):
@@ -102,7 +105,7 @@ def partition(H, nranks):
         isf, isc = np.asarray(lv.is_fine, dtype=np.int64), np.asarray(lv.is_coarse, dtype=np.int64)
         rf = np.searchsorted(isf, rv)          # F ownership offsets
         rc = np.searchsorted(isc, rv)          # C ownership offsets == next level's row ownership
-        for r in range(nranks):
+        for r in todo:
             a, b = rv[r], rv[r + 1]
             d = {"n": int(b - a), "rstart": int(a), "smooth": list(lv.smooth_order),
                  "is_fine": (isf[rf[r]:rf[r + 1]] - a).astype(np.int32),
@@ -124,7 +127,7 @@ def partition(H, nranks):
             out[r].rangesV.append(rv.copy())
             out[r].rangesF.append(rf.copy())
         rv = rc
-    for r in range(nranks):
+    for r in todo:
         a, b = rv[r], rv[r + 1]
         d = {"n": int(b - a), "rstart": int(a), "smooth": [], "is_fine": np.zeros(0, np.int32),
              "is_coarse": np.zeros(0, np.int32), "ops": {}}

@@ -23,12 +23,17 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
-    uid = [None]
-    if rank == 0:
-        buf = ctypes.create_string_buffer(128)
-        _capi.check(_capi.lib().pflare_b200_get_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
-        uid[0] = buf.raw
-    dist.broadcast_object_list(uid, src=0)
+
+    def fresh_uid():
+        """one NCCL unique id per communicator (= per PC), made on rank 0 and broadcast by the host communicator"""
+        uid = [None]
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            _capi.check(_capi.lib().pflare_b200_get_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+            uid[0] = buf.raw
+        dist.broadcast_object_list(uid, src=0)
+        return uid[0]
+
     worst = 0.0
     for name in ("fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "dg_mf"):
         A, H = cases.build(name)
@@ -37,7 +42,7 @@ def main():
         parts = hiergen.partition(H, world)
         rg = parts[0].rangesV[0]
         for agg_rows in (0, 600):
-            pc = pflare_b200.PC(rank=rank, nranks=world, unique_id=uid[0], device=local).setType("air").setHierarchy(parts[rank])
+            pc = pflare_b200.PC(rank=rank, nranks=world, unique_id=fresh_uid(), device=local).setType("air").setHierarchy(parts[rank])
             pc.setOption("agg_rows", agg_rows)
             x = pc.apply(b[rg[rank]:rg[rank + 1]])
             err = np.linalg.norm(x - xo[rg[rank]:rg[rank + 1]]) / np.linalg.norm(xo)

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 for cfg in "$@"; do
   o=""; for kv in $cfg; do o="$o --opt $kv"; done
   tag=$(echo $cfg | tr ' =' '__')
-  timeout 900 python bench.py --n $N --steps 20 --warmup 3 --no-cpu-baseline --dump-ops gpurun_out/ops_${N}_$tag.csv $o > gpurun_out/s_${N}_$tag.json 2> gpurun_out/s_${N}_$tag.log || echo FAIL $cfg
+  timeout 900 python bench.py --size $N --steps 20 --warmup 3 --no-cpu-baseline --dump-ops gpurun_out/ops_${N}_$tag.csv $o > gpurun_out/s_${N}_$tag.json 2> gpurun_out/s_${N}_$tag.log || echo FAIL $cfg
   python - gpurun_out/s_${N}_$tag.json <<'PY'
 import json,sys
 try:
