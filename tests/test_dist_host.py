@@ -1,0 +1,124 @@
+"""CPU suite, part 3: the multi-rank HOST logic of the product (no GPU): MPIAIJ partitioning, ghost
+plans, agglomeration layout -- through the in-process rank group (threads) and through a world_size-2
+gloo group (torchrun) in host-only planning mode."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cases
+import hiergen
+import pflare_b200
+from dist_emul import distributed_products
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reassemble(parts, l, which, shape):
+    blocks = []
+    for lh in parts:
+        op = lh.levels[l - 1]["ops"][which]
+        d = op.diag.tocoo()
+        rows, cols, vals = [d.row], [d.col + op.cstart], [d.data]
+        if op.offdiag is not None:
+            o = op.offdiag.tocoo()
+            rows.append(o.row); cols.append(op.garray[o.col]); vals.append(o.data)
+        blocks.append(sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                                    shape=(op.diag.shape[0], shape[1])))
+    return sp.vstack(blocks).tocsr()
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 5])
+def test_partition_reassembles_bit_exactly(nranks):
+    A, H = cases.build("fd2d_fcf")
+    parts = hiergen.partition(H, nranks)
+    for l, lv in enumerate(H.levels, start=1):
+        for which, M in ((pflare_b200.AFF, lv.A_ff), (pflare_b200.AFC, lv.A_fc), (pflare_b200.ACF, lv.A_cf),
+                         (pflare_b200.ACC, lv.A_cc), (pflare_b200.R, lv.R), (pflare_b200.P, lv.P)):
+            B = _reassemble(parts, l, which, M.shape)
+            assert (B != M).nnz == 0 and B.nnz == M.nnz
+        # index sets: local lists + rstart reproduce the serial lists
+        isf = np.concatenate([lh.levels[l - 1]["is_fine"] + lh.levels[l - 1]["rstart"] for lh in parts])
+        assert np.array_equal(isf, lv.is_fine)
+        # garray sorted, strictly increasing, never a local column (PETSc's convention)
+        for lh in parts:
+            for op in lh.levels[l - 1]["ops"].values():
+                g = op.garray
+                assert np.all(np.diff(g) > 0)
+                assert not np.any((g >= op.cstart) & (g < op.cstart + op.diag.shape[1]))
+
+
+@pytest.mark.parametrize("name,nranks,agg_rows", [("fd2d_64", 2, 0), ("fd2d_64", 4, 700), ("fd3d_10_lump", 3, 0),
+                                                   ("fd2d_fcf", 3, 200), ("dg_mf", 2, 10 ** 9), ("fd2d_25", 7, 0)])
+def test_ghost_plans_in_process_group(built_libs, name, nranks, agg_rows):
+    """Host-only planning group: plans are symmetric and drive correct distributed products."""
+    A, H = cases.build(name)
+    parts = hiergen.partition(H, nranks)
+    cl = pflare_b200.ClusterAIR(H.no_levels, nranks, device=-1)
+    cl.set_option("agg_rows", agg_rows)
+    cl.upload(parts)
+    l_agg, rows = cl.ranks[0].layout()
+    assert list(rows) == H.sizes()
+    if agg_rows == 0:
+        assert l_agg == H.no_levels + 1
+    else:
+        assert l_agg == next((l for l in range(2, H.no_levels + 1) if H.sizes()[l - 1] <= agg_rows), H.no_levels + 1)
+    nl = min(l_agg, H.no_levels)
+    for l in range(1, nl):
+        for which in (pflare_b200.AFF, pflare_b200.AFC, pflare_b200.R, pflare_b200.P):
+            plans = [r.ghost_plan(l, which) for r in cl.ranks]
+            for p in range(nranks):
+                for q in range(nranks):
+                    assert plans[p]["send_count"][q] == plans[q]["recv_count"][p]
+                assert plans[p]["send_idx"].size == plans[p]["send_count"].sum()
+
+    # the plans drive correct distributed products (exchange emulated in-process: rank r receives
+    # exactly what rank p packed for it)
+    worst = max(_products_with_lookup(H, parts, r, nranks, cl, l_agg) for r in range(nranks))
+    assert worst < 1e-13
+    # no GPU bound: apply must refuse
+    with pytest.raises(pflare_b200.PflareB200Error):
+        cl.apply([np.zeros(p.local_rows()) for p in parts])
+    cl.close()
+
+
+def _products_with_lookup(H, parts, rank, world, cl, l_agg):
+    """distributed_products with an exchange that looks the peers' packed chunks up directly."""
+    state = {}
+
+    def exchange(sendbufs, recvcounts):
+        # called once per (level, operator) in a fixed order; replay the same order on every peer
+        k = state.setdefault("k", 0)
+        state["k"] = k + 1
+        out = []
+        for p in range(world):
+            if p == rank or not recvcounts[p]:
+                out.append(np.zeros(0))
+                continue
+            out.append(_PACKS[(id(cl), p)][k][rank])
+        return out
+
+    # make sure every peer's packs exist
+    for p in range(world):
+        key = (id(cl), p)
+        if key not in _PACKS:
+            rec = []
+            distributed_products(H, parts, p, world, cl.ranks[p], l_agg,
+                                 exchange=lambda sendbufs, recvcounts, rec=rec: (rec.append(sendbufs), [np.zeros(int(c)) for c in recvcounts])[1])
+            _PACKS[key] = rec
+    return distributed_products(H, parts, rank, world, cl.ranks[rank], l_agg, exchange)
+
+
+_PACKS = {}
+
+
+def test_gloo_two_processes(built_libs):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_gloo_check.py")]
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "GLOO_DIST_OK" in out.stdout
