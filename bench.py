@@ -296,6 +296,12 @@ def run_gpu(args):
     with ClockSampler(local) as clk:
         ms_dev = timed(lambda: dev.apply_ptr(b.data_ptr(), x.data_ptr(), 1), args.steps, args.warmup)
     clocks = clk.summary()
+    extra = {}
+    for kv in args.compare_opt:
+        k, v = kv.split("=")
+        pc.setOption(k, float(v))
+        extra[kv] = timed(lambda: dev.apply_ptr(b.data_ptr(), x.data_ptr(), 1), args.steps, args.warmup)
+        log("[bench] with %s: %.4f ms per V-cycle (main run %.4f)" % (kv, extra[kv], ms_dev))
     # end-to-end leg: host (pinned) buffers through the reference-facing call
     ms_e2e = timed(lambda: dev.apply_ptr(b_host.data_ptr(), x_host.data_ptr(), 0), args.steps, args.warmup)
 
@@ -401,6 +407,7 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-cache", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
+    ap.add_argument("--compare-opt", action="append", default=[], help="after the main run, re-time the device-resident leg with this option changed (key=value)")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch table of one V-cycle (CUDA events) to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -397,6 +397,37 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(const EwOp e) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += gridDim.x * blockDim.x) ew_apply(e, i);
 }
 
+// Dense collapsed tail: y = T x, T row-major n x n.  One warp per row, fixed summation order
+// (8 interleaved partial sums per lane, then a shuffle tree) -> deterministic.
+__global__ void __launch_bounds__(kThreads) dense_gemv_kernel(int n, const double *__restrict__ T, const double *__restrict__ x,
+                                                              double *__restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < n; row += nwarps) {
+    const double *t = T + (size_t)row * n;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int j = lane;
+    for (; j + 7 * 32 < n; j += 8 * 32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += __ldcs(t + j + u * 32) * x[j + u * 32];
+    }
+    for (int u = 0; j < n; j += 32, ++u) acc[u] += __ldcs(t + j) * x[j];
+    double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+  }
+}
+
+// setup helpers of the dense tail: unit vector, strided column store
+__global__ void unit_vector_kernel(int n, int j, double *v) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = (i == j) ? 1.0 : 0.0;
+}
+__global__ void store_column_kernel(int n, int j, const double *v, double *T) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) T[(size_t)i * n + j] = v[i];
+}
+
 // Single-CTA "tail": runs a whole list of ops (the small coarse levels: restrictions, coarse
 // solve, prolongation + smoothing) back to back with CTA barriers instead of kernel launches.
 __global__ void __launch_bounds__(kTailThreads) tail_kernel(const DevOp *ops, int nops) {

@@ -148,7 +148,7 @@ struct Level {
   bool any_c = false;
 };
 
-enum { OPK_SPMV = 0, OPK_EW = 1, OPK_XCHG = 2, OPK_GATHER0 = 3, OPK_SCATTER0 = 4, OPK_CHILD = 5 };
+enum { OPK_SPMV = 0, OPK_EW = 1, OPK_XCHG = 2, OPK_GATHER0 = 3, OPK_SCATTER0 = 4, OPK_CHILD = 5, OPK_DENSE = 6 };
 
 struct Op {
   int kind = OPK_SPMV;
@@ -157,7 +157,7 @@ struct Op {
   DevPlan *xp = nullptr;        // OPK_XCHG: which plan; xsrc = the vector segment being exchanged
   const double *xsrc = nullptr;
   int level = 0;
-  int tag = 0;  // 1 restrict, 2 coarse, 3 A_fc(+W), 4 A_ff residual, 5 inverse, 6 elementwise, 7 fused local smooth, 8 A_cf, 9 A_cc, 10 exchange
+  int tag = 0;  // 1 restrict, 2 coarse, 3 A_fc(+W), 4 A_ff residual, 5 inverse, 6 elementwise, 7 fused local smooth, 8 A_cf, 9 A_cc, 10 exchange, 11 dense tail
   double bytes = 0, nnz = 0;
 };
 
@@ -181,6 +181,11 @@ struct Ctx {
   int tail_begin = -1, tail_end = -1;  // [begin,end) range of ops executed by the tail kernel
   DevOp *d_tail = nullptr;
   int tail_levels = 0;
+  // dense collapsed tail: the sub-cycle of levels >= dense_level as ONE n x n matrix (x_l = T b_l)
+  std::vector<Op> dense_prog;           // the ops it replaces (run once per unit vector at setup)
+  int dense_level = 0, dense_n = 0;
+  double *dense_T = nullptr;
+  bool dense_built = false;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   int graph_kernels = 0;
@@ -188,6 +193,7 @@ struct Ctx {
   int use_graph = 1, fuse = 1;
   int tail_rows = 2048;
   int64_t tail_nnz = 40000;
+  int dense_rows = 0;    // levels with <= this many rows are collapsed into a dense matrix (0 = off)
   int kernel = 1;        // 0: smem-staged stream kernel, 1..: TMA-pipelined variants (kVariants)
   int tile_kernel = 1;   // the variant the uploaded tile lists were built for
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
@@ -766,6 +772,11 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
     if (o.e.n == 0) return 0;
     int grid = std::min((o.e.n + kThreads - 1) / kThreads, c->num_sms * 8);
     ew_kernel<<<grid, kThreads, 0, st>>>(o.e);
+  } else if (o.kind == OPK_DENSE) {
+    if (dry) return 0;
+    const int n = c->dense_n;
+    int grid = std::min((n * 32 + kThreads - 1) / kThreads, c->num_sms * 8);
+    dense_gemv_kernel<<<grid, kThreads, 0, st>>>(n, c->dense_T, o.e.a, o.e.out);
   } else {
     return fail(7, "internal: op kind %d cannot be launched directly", o.kind);
   }
@@ -803,7 +814,7 @@ int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op
   const int nr = (int)R.size();
   for (int i = begin; i < end; ++i) {
     const int kind = (*progs[0])[i].kind;
-    if (kind == OPK_SPMV || kind == OPK_EW) {
+    if (kind == OPK_SPMV || kind == OPK_EW || kind == OPK_DENSE) {
       for (int r = 0; r < nr; ++r) {
         const Op &o = (*progs[r])[i];
         if (op_is_empty(o)) continue;
@@ -948,10 +959,17 @@ int build_program(Ctx *c) {
     }
   }
   c->tail_levels = (ltail <= NL) ? NL - ltail + 1 : 0;
+  // dense collapsed tail (serial contexts): the longest suffix of levels with <= dense_rows rows
+  int ldense = NL + 1, dense_begin = -1, dense_end = -1;
+  if (c->nranks == 1 && c->dense_rows > 0 && c->device >= 0) {
+    for (int l = NL; l >= 1; --l) { if (c->L[l].n <= c->dense_rows) ldense = l; else break; }
+    if (ldense > ltail || ldense > NL - 1) ldense = NL + 1;   // must contain the single-CTA tail and >= 2 levels
+  }
   // down: b_{l+1} = b_c + Z b_f  (MatRestrict with R = [Z I])
   for (int l = 1; l <= LB - 1; ++l) {
     Level &Lv = c->L[l];
     B.level = l;
+    if (l == ldense) dense_begin = (int)c->prog.size();
     if (l == ltail) c->tail_begin = (int)c->prog.size();
     if (Lv.any_c) B.push_ew(Lv.nc, c->bb + Lv.off + Lv.nf, nullptr, nullptr, 1.0, Lv.bc_save, 1);
     SpmvOp s = B.base(Lv.Z, c->bb + Lv.off);
@@ -979,6 +997,25 @@ int build_program(Ctx *c) {
     int rc = B.emit_fc_richardson(Lv, true);
     if (rc) return rc;
     if (l == ltail) c->tail_end = (int)c->prog.size();
+    if (l == ldense) dense_end = (int)c->prog.size();
+  }
+  if (dense_begin >= 0 && dense_end > dense_begin + 1) {
+    // replace the ops of levels >= ldense by ONE dense product x_l = T b_l; T is built at setup by
+    // running exactly these ops on the unit vectors (build_dense_tail)
+    Level &Ld = c->L[ldense];
+    std::vector<Op> sub(c->prog.begin() + dense_begin, c->prog.begin() + dense_end);
+    Op d; d.kind = OPK_DENSE; d.level = ldense; d.tag = 11;
+    d.e.n = Ld.n; d.e.a = c->bb + Ld.off; d.e.out = c->xb + Ld.off;
+    for (const Op &o : sub) { d.bytes += o.bytes; d.nnz += o.nnz; }
+    c->prog.erase(c->prog.begin() + dense_begin, c->prog.begin() + dense_end);
+    c->prog.insert(c->prog.begin() + dense_begin, d);
+    if (c->dense_level != ldense || c->dense_n != Ld.n) c->dense_built = false;
+    c->dense_prog.swap(sub);
+    c->dense_level = ldense; c->dense_n = Ld.n;
+    c->tail_begin = c->tail_end = -1;   // superseded
+    c->tail_levels = NL - ldense + 1;
+  } else {
+    c->dense_prog.clear(); c->dense_level = 0; c->dense_n = 0;
   }
   if (ltail == NL && c->tail_begin >= 0) c->tail_end = c->tail_begin;  // coarse level alone: not worth a tail
   if (c->device >= 0 && c->tail_begin >= 0 && c->tail_end > c->tail_begin) {
@@ -998,6 +1035,29 @@ int build_program(Ctx *c) {
   for (const Op &o : c->prog)
     if (o.kind == OPK_XCHG) { c->ghost_bytes += 8.0 * o.xp->plan.n_send(); ++c->xchg_groups; }
     else if (o.kind == OPK_GATHER0 || o.kind == OPK_SCATTER0) { c->ghost_bytes += o.bytes; ++c->xchg_groups; }
+  return 0;
+}
+
+// T = the linear map b_l -> x_l of the sub-cycle over levels >= dense_level, column by column
+int build_dense_tail(Ctx *c) {
+  if (c->dense_prog.empty() || c->dense_built) return 0;
+  const int n = c->dense_n;
+  Level &Ld = c->L[c->dense_level];
+  int rc;
+  if (!c->dense_T && (rc = dev_alloc(c, &c->dense_T, (size_t)n * n))) return rc;
+  { Op dummy; if ((rc = launch_op(c, dummy, c->stream, true))) return rc; }
+  std::vector<Ctx *> R{c};
+  std::vector<const std::vector<Op> *> P{&c->dense_prog};
+  const int grid = std::min((n + kThreads - 1) / kThreads, c->num_sms * 8);
+  for (int j = 0; j < n; ++j) {
+    unit_vector_kernel<<<grid, kThreads, 0, c->stream>>>(n, j, c->bb + Ld.off);
+    if ((rc = exec_ops(R, P, 0, (int)c->dense_prog.size(), c->stream))) return rc;
+    store_column_kernel<<<grid, kThreads, 0, c->stream>>>(n, j, c->xb + Ld.off, c->dense_T);
+    if ((j & 255) == 255) CUDA_TRY(cudaStreamSynchronize(c->stream));   // bound the launch queue
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->dense_built = true;
   return 0;
 }
 
@@ -1067,7 +1127,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->rank = 0; ch->nranks = 1; ch->device = c->device; ch->no_levels = NL - LA + 1;
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
-  ch->use_graph = 0; ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz;
+  ch->use_graph = 0; ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->dense_rows = c->dense_rows;
   ch->kernel = c->kernel; ch->tile_kernel = c->tile_kernel; ch->ctas_per_sm = c->ctas_per_sm;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
@@ -1490,6 +1550,7 @@ int finalize_ctx(Ctx *c) {
   }
   // ---- (4) program + graph
   if ((rc = build_program(c))) return rc;
+  if ((rc = build_dense_tail(c))) return rc;
   if (c->use_graph && NL >= 2 && !c->cluster) {
     if ((rc = build_graph(c))) return rc;
   }
@@ -1911,6 +1972,10 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else if (k == "fuse") c->fuse = value != 0;
   else if (k == "tail_rows") c->tail_rows = (int)value;
   else if (k == "tail_nnz") c->tail_nnz = (int64_t)value;
+  else if (k == "dense_rows") {
+    if (value > 16384) return fail(2, "dense_rows is limited to 16384 (the collapsed tail is a dense n x n fp64 matrix)");
+    c->dense_rows = (int)value;
+  }
   else if (k == "agg_rows") {
     if (c->finalized || c->planned) return fail(2, "agg_rows must be set before finalize_setup");
     c->agg_rows = (int64_t)value;
@@ -1928,16 +1993,20 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   if (c->child) {
     Ctx *ch = c->child.get();
     ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->kernel = c->kernel; ch->ctas_per_sm = c->ctas_per_sm;
-    ch->dbg_seq = c->dbg_seq;
+    ch->dbg_seq = c->dbg_seq; ch->dense_rows = c->dense_rows;
   }
   return 0;
 }
 
 static int rebuild_after_option(Ctx *c) {
   int rc;
-  if (c->child && c->child->finalized && (rc = build_program(c->child.get()))) return rc;
+  if (c->child && c->child->finalized) {
+    if ((rc = build_program(c->child.get()))) return rc;
+    if ((rc = build_dense_tail(c->child.get()))) return rc;
+  }
   if (c->finalized) {
     if ((rc = build_program(c))) return rc;
+    if ((rc = build_dense_tail(c))) return rc;
     if (c->use_graph && c->no_levels >= 2 && !c->cluster) { if ((rc = build_graph(c))) return rc; }
   }
   return 0;

@@ -51,7 +51,7 @@ def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
         assert all(s["exchange_groups"] > 0 for s in stats)
 
 
-@pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=5)], ids=str)
+@pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=5), dict(dense_rows=4096)], ids=str)
 def test_partitioned_execution_modes(built_libs, opts):
     A, H = cases.build("fd2d_64")
     b = cases.rhs(A.shape[0], seed=3)

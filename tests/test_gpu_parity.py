@@ -56,7 +56,9 @@ def test_vcycle_parity(built_libs, name):
                                   dict(kernel=6, tail_rows=0), dict(kernel=7, tail_rows=0), dict(kernel=8, tail_rows=0),
                                   dict(kernel=9, tail_rows=0), dict(kernel=10, tail_rows=0), dict(kernel=11, tail_rows=0),
                                   dict(kernel=12, tail_rows=0), dict(kernel=13, tail_rows=0),
-                                  dict(kernel=2, ctas_per_sm=1)],
+                                  dict(kernel=2, ctas_per_sm=1),
+                                  # coarse levels collapsed into one dense operator (built from the same kernels at setup)
+                                  dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, tail_rows=0, graph=0)],
                          ids=lambda o: ",".join("%s=%g" % kv for kv in o.items()))
 @pytest.mark.parametrize("name", ["fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "fd2d_diagAff", "dg_mf", "fd2d_idealW"])
 def test_vcycle_parity_execution_modes(built_libs, name, opts):
@@ -194,6 +196,8 @@ def test_medium_size_parity_and_linearity(built_libs):
     assert cases.rel_l2(x1, _oracle(H).apply(b1)) <= TOL
     x12 = d.apply(2.5 * b1 - b2)
     assert cases.rel_l2(x12, 2.5 * x1 - x2) <= 1e-11
+    d.set_option("dense_rows", 4096)        # collapsed coarse tail: same answer to round-off
+    assert cases.rel_l2(d.apply(b1), x1) <= TOL
     st = d.stats()
     assert st["kernel_launches"] > 0 and st["algorithmic_bytes"] > 12 * st["nnz_per_cycle"]
     d.close()
