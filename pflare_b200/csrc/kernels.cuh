@@ -384,6 +384,146 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Second TMA kernel: NOTHING in a tile's processing waits on global memory.
+//   * matrix stream (values, columns, row pointers): TMA bulk copies, STAGES-deep ring (as above);
+//   * x gathers of tile t+1: issued as 8-byte cp.async (LDGSTS) into a double-buffered shared array
+//     while tile t is being reduced -- the dependent gather latency is off the critical path;
+//   * epilogue operands of tile t+1: register prefetch one tile ahead;
+//   * multiply + reduce fused: g lanes per row (g = largest power of two with rows*g <= NT, <= 32)
+//     read values and gathered x from shared memory, shuffle-reduce, lane 0 runs the epilogue.
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NT, int TILE, int STAGES>
+__global__ void __launch_bounds__(NT) spmv_tma2_kernel(const SpmvOp op) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  typedef TmaStage<TILE, NT> Stage;
+  Stage *stages = reinterpret_cast<Stage *>(smem_raw);
+  double *xring = reinterpret_cast<double *>(smem_raw + sizeof(Stage) * STAGES);   // [2][TILE]
+  __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ TileDesc sdesc[STAGES];
+  __shared__ double red[NT / 32 + 1];
+  const int tid = threadIdx.x;
+  const TileDesc *__restrict__ tiles = op.tiles;
+  const int ntiles = op.ntiles;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_tiles = (first < ntiles) ? (ntiles - first + stride - 1) / stride : 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint64_t pol = l2_policy_evict_first();
+  TileDesc dnext = {0, 0, 0, 0};
+  if (tid == 0 && my_tiles > 0) dnext = tiles[first];
+  auto issue = [&](int j) {
+    const TileDesc d = dnext;
+    if (j + 1 < my_tiles) dnext = tiles[first + (j + 1) * stride];
+    const int slot = j % STAGES;
+    sdesc[slot] = d;
+    if (d.n <= TILE) {
+      Stage &S = stages[slot];
+      const int s_al = d.s & ~3;
+      const int cnt = (d.n + (d.s - s_al) + 3) & ~3;
+      const int r_al = d.r0 & ~3;
+      const int rcnt = (d.nrows + 1 + (d.r0 - r_al) + 3) & ~3;
+      mbar_expect_tx(&full[slot], (uint32_t)(cnt * 12 + rcnt * 4));
+      tma_load_1d(S.val, op.val + s_al, (uint32_t)(cnt * 8), &full[slot], pol);
+      tma_load_1d(S.col, op.col + s_al, (uint32_t)(cnt * 4), &full[slot], pol);
+      tma_load_1d(S.rp, op.rp + r_al, (uint32_t)(rcnt * 4), &full[slot], pol);
+    } else {
+      mbar_expect_tx(&full[slot], 0);
+    }
+  };
+  // lanes per row of a tile
+  auto lanes_per_row = [](int nrows) { int g = 1; while (g < 32 && nrows * (g << 1) <= NT) g <<= 1; return g; };
+  // stage the gathers + epilogue operands of local tile j (its matrix data must have landed)
+  EpiPre pre_next;
+  auto stage_gathers = [&](int j) {
+    const int slot = j % STAGES;
+    const TileDesc d = sdesc[slot];
+    mbar_wait(&full[slot], (uint32_t)((j / STAGES) & 1));
+    if (d.n <= TILE) {
+      const Stage &S = stages[slot];
+      double *xs = xring + (j & 1) * TILE;
+      const int o = d.s & 3;
+      constexpr int kIter = TILE / NT;
+#pragma unroll
+      for (int k0 = 0; k0 < kIter; ++k0) {
+        const int k = tid + k0 * NT;
+        if (k < d.n) {
+          const int c = S.col[o + k];
+          const double *src = (op.xg != nullptr && c >= op.nloc) ? op.xg + (c - op.nloc) : op.x + c;
+          cp_async8(xs + k, src);
+        }
+      }
+      const int g = lanes_per_row(d.nrows);
+      if (tid < d.nrows * g && (tid & (g - 1)) == 0) pre_next = epi_prefetch(op, d.r0 + tid / g);
+    }
+    cp_async_commit();
+  };
+  if (tid == 0) {
+    for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);
+  }
+  __syncthreads();
+  if (my_tiles > 0) stage_gathers(0);
+
+  for (int it = 0; it < my_tiles; ++it) {
+    const int slot = it % STAGES;
+    if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);  // slot freed by the barrier ending iteration it-1
+    const TileDesc d = sdesc[slot];
+    Stage &S = stages[slot];
+    const EpiPre pre = pre_next;
+    if (it + 1 < my_tiles) { stage_gathers(it + 1); cp_async_wait<1>(); }   // tile it's gathers are complete, tile it+1's in flight
+    else cp_async_wait<0>();
+    __syncthreads();
+    if (d.n <= TILE) {
+      const double *xs = xring + (it & 1) * TILE;
+      const int o = d.s & 3;
+      const int g = lanes_per_row(d.nrows);
+      const bool active = tid < d.nrows * g;
+      const int row = tid / g, lg = tid & (g - 1);
+      int p = 0, q = 0;
+      if (active) {
+        const int ro = d.r0 & 3;
+        p = S.rp[ro + row] - d.s;      // tile-relative
+        q = S.rp[ro + row + 1] - d.s;
+      }
+      const int qs = op.wlast ? q - 1 : q;
+      double sum = 0.0, xw = 0.0;
+      for (int k = p + lg; k < qs; k += g) sum += S.val[o + k] * xs[k];
+      if (op.wlast && active && lg == ((qs - p) & (g - 1))) xw = S.val[o + qs] * xs[qs];
+      for (int w = g >> 1; w > 0; w >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, w, g);
+        if (op.wlast) xw += __shfl_down_sync(0xffffffffu, xw, w, g);
+      }
+      if (active && lg == 0) epi_finish(op, d.r0 + row, sum, xw, pre);
+    } else {
+      const int e = d.s + d.n;
+      const int last = op.wlast ? e - 1 : e;
+      double part = 0.0;
+      for (int k = d.s + tid; k < last; k += NT) part += ld_stream(op.val + k) * gather_x(op, ld_stream(op.col + k));
+#pragma unroll
+      for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(0xffffffffu, part, w);
+      if ((tid & 31) == 0) red[tid >> 5] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < NT / 32; ++w) sum += red[w];
+        const double xw = op.wlast ? op.val[last] * gather_x(op, op.col[last]) : 0.0;
+        row_epilogue(op, d.r0, sum, xw);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
+}
+
 __device__ __forceinline__ void ew_apply(const EwOp &e, int i) {
   double v = e.alpha * e.a[e.gather ? e.gather[i] : i];
   if (e.b) v = v * e.b[i];

@@ -67,7 +67,8 @@ const double kTolZero = (double)1e-12f;
 struct Variant { int nt, tile, stages; };
 const Variant kVariants[] = {{0, 0, 0}, {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {256, 2048, 3}, {512, 2048, 2}, {512, 4096, 2}, {128, 512, 3}, {128, 1024, 4},
                              {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {512, 2048, 2}, {128, 512, 3},   // 9..13: row-mapped multiply
-                             {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 3}, {128, 512, 2}, {128, 512, 3}};  // 14..19: register-capped for more resident CTAs
+                             {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 3}, {128, 512, 2}, {128, 512, 3},  // 14..19: register-capped for more resident CTAs
+                             {256, 1024, 3}, {256, 1024, 4}, {256, 2048, 3}, {512, 2048, 3}, {128, 512, 4}};  // 20..24: asynchronous gathers (spmv_tma2_kernel)
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
 struct HostCSR {
@@ -185,6 +186,7 @@ struct Ctx {
   std::vector<Op> dense_prog;           // the ops it replaces (run once per unit vector at setup)
   int dense_level = 0, dense_n = 0;
   double *dense_T = nullptr;
+  size_t dense_cap = 0;                 // entries allocated for dense_T
   bool dense_built = false;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -719,6 +721,24 @@ int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   return 0;
 }
 
+template <int NT, int TILE, int STAGES>
+int launch_tma2(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  auto kern = spmv_tma2_kernel<NT, TILE, STAGES>;
+  const size_t smem = sizeof(TmaStage<TILE, NT>) * STAGES + 2 * TILE * sizeof(double);
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem));
+    per_sm = std::max(nb, 1);
+  }
+  if (dry) return 0;
+  const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
+  const int grid = std::min(s.ntiles, c->num_sms * want);
+  kern<<<grid, NT, smem, st>>>(s);
+  return 0;
+}
+
 __global__ void __launch_bounds__(kThreads) pack_kernel(int n, const int *__restrict__ idx, const double *__restrict__ x, double *__restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];
 }
@@ -763,6 +783,11 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
       case 17: rc = launch_tma<256, 1024, 3, false, 5>(c, o.s, st, dry); break;
       case 18: rc = launch_tma<128, 512, 2, false, 16>(c, o.s, st, dry); break;
       case 19: rc = launch_tma<128, 512, 3, false, 12>(c, o.s, st, dry); break;
+      case 20: rc = launch_tma2<256, 1024, 3>(c, o.s, st, dry); break;
+      case 21: rc = launch_tma2<256, 1024, 4>(c, o.s, st, dry); break;
+      case 22: rc = launch_tma2<256, 2048, 3>(c, o.s, st, dry); break;
+      case 23: rc = launch_tma2<512, 2048, 3>(c, o.s, st, dry); break;
+      case 24: rc = launch_tma2<128, 512, 4>(c, o.s, st, dry); break;
       default: return fail(2, "unknown kernel variant %d", k);
     }
     if (rc) return rc;
@@ -1044,7 +1069,10 @@ int build_dense_tail(Ctx *c) {
   const int n = c->dense_n;
   Level &Ld = c->L[c->dense_level];
   int rc;
-  if (!c->dense_T && (rc = dev_alloc(c, &c->dense_T, (size_t)n * n))) return rc;
+  if (c->dense_cap < (size_t)n * n) {   // (a superseded smaller matrix stays in the context's allocation list until destroy)
+    if ((rc = dev_alloc(c, &c->dense_T, (size_t)n * n))) return rc;
+    c->dense_cap = (size_t)n * n;
+  }
   { Op dummy; if ((rc = launch_op(c, dummy, c->stream, true))) return rc; }
   std::vector<Ctx *> R{c};
   std::vector<const std::vector<Op> *> P{&c->dense_prog};

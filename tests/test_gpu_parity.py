@@ -56,6 +56,9 @@ def test_vcycle_parity(built_libs, name):
                                   dict(kernel=6, tail_rows=0), dict(kernel=7, tail_rows=0), dict(kernel=8, tail_rows=0),
                                   dict(kernel=9, tail_rows=0), dict(kernel=10, tail_rows=0), dict(kernel=11, tail_rows=0),
                                   dict(kernel=12, tail_rows=0), dict(kernel=13, tail_rows=0),
+                                  # 20..24: spmv_tma2_kernel (asynchronous cp.async gathers, fused multiply/reduce)
+                                  dict(kernel=20, tail_rows=0), dict(kernel=21, tail_rows=0), dict(kernel=22, tail_rows=0),
+                                  dict(kernel=23, tail_rows=0), dict(kernel=24, tail_rows=0),
                                   dict(kernel=2, ctas_per_sm=1),
                                   # coarse levels collapsed into one dense operator (built from the same kernels at setup)
                                   dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, tail_rows=0, graph=0)],
