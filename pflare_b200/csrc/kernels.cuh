@@ -72,6 +72,13 @@ struct DevOp {
   EwOp e;
 };
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
+// attribute may start while its predecessor drains; everything before pdl_wait() must touch only
+// data no kernel of the cycle writes (matrix arrays, tile lists), everything after sees the
+// predecessor's results.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
@@ -170,6 +177,8 @@ __device__ __forceinline__ void process_block(const SpmvOp &op, int b, double *p
 }
 
 __global__ void __launch_bounds__(kThreads) spmv_stream_kernel(const SpmvOp op) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double prod[kTile];
   __shared__ double red[kThreads / 32];
   for (int b = blockIdx.x; b < op.nblk; b += gridDim.x) process_block<kThreads>(op, b, prod, red);
@@ -277,9 +286,11 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
       mbar_expect_tx(&full[slot], 0);  // long row: streamed straight from global by the whole CTA
     }
   };
+  pdl_launch_dependents();
   if (tid == 0) {
-    for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);
+    for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);   // matrix data only: legal before pdl_wait
   }
+  pdl_wait();   // from here on the vectors written by the previous kernels are read
   __syncthreads();
 
   for (int it = 0; it < my_tiles; ++it) {
@@ -467,9 +478,11 @@ __global__ void __launch_bounds__(NT) spmv_tma2_kernel(const SpmvOp op) {
     }
     cp_async_commit();
   };
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);
   }
+  pdl_wait();
   __syncthreads();
   if (my_tiles > 0) stage_gathers(0);
 
@@ -534,6 +547,8 @@ __device__ __forceinline__ void ew_apply(const EwOp &e, int i) {
 }
 
 __global__ void __launch_bounds__(kThreads) ew_kernel(const EwOp e) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += gridDim.x * blockDim.x) ew_apply(e, i);
 }
 
@@ -541,6 +556,8 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(const EwOp e) {
 // (8 interleaved partial sums per lane, then a shuffle tree) -> deterministic.
 __global__ void __launch_bounds__(kThreads) dense_gemv_kernel(int n, const double *__restrict__ T, const double *__restrict__ x,
                                                               double *__restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -571,6 +588,8 @@ __global__ void store_column_kernel(int n, int j, const double *v, double *T) {
 // Single-CTA "tail": runs a whole list of ops (the small coarse levels: restrictions, coarse
 // solve, prolongation + smoothing) back to back with CTA barriers instead of kernel launches.
 __global__ void __launch_bounds__(kTailThreads) tail_kernel(const DevOp *ops, int nops) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double prod[kTile];
   __shared__ double red[kTailThreads / 32];
   for (int o = 0; o < nops; ++o) {

@@ -193,13 +193,14 @@ struct Ctx {
   int graph_kernels = 0;
   // options
   int use_graph = 1, fuse = 1;
-  int tail_rows = 2048;
+  int tail_rows = 0;     // levels with <= this many rows run in the single-CTA tail kernel (0 = off: measured slower than graph nodes)
   int64_t tail_nnz = 40000;
-  int dense_rows = 0;    // levels with <= this many rows are collapsed into a dense matrix (0 = off)
+  int dense_rows = 4096; // levels with <= this many rows are collapsed into one dense matrix (0 = off)
   int kernel = 1;        // 0: smem-staged stream kernel, 1..: TMA-pipelined variants (kVariants)
   int tile_kernel = 1;   // the variant the uploaded tile lists were built for
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int dbg_seq = 0;       // measurement only (wrong results): sequential instead of indexed x gathers
+  int pdl = 1;           // programmatic dependent launch between the kernels of the cycle
   int64_t agg_rows = 262144;  // levels with <= this many GLOBAL rows are agglomerated onto rank 0 (multi-rank)
   int num_sms = 148;
   // multi-rank
@@ -703,6 +704,19 @@ struct NcclHostComm : HostComm {
 };
 
 // ------------------------------------------------------------------ launching
+// Every kernel of the cycle goes through here: with option pdl=1 the launch carries the
+// programmatic-stream-serialization attribute (PDL), so a kernel's prologue (mbarrier init, tile
+// descriptors, the first TMA bulk copies of constant matrix data) overlaps the predecessor's drain.
+template <class K, class... Args>
+cudaError_t launch_k(bool pdl, K kern, int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 template <int NT, int TILE, int STAGES, bool ROWMAP = false, int MINB = 1>
 int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   auto kern = spmv_tma_kernel<NT, TILE, STAGES, ROWMAP, MINB>;
@@ -717,7 +731,7 @@ int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   if (dry) return 0;
   const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
   const int grid = std::min(s.ntiles, c->num_sms * want);   // persistent: a multiple of the SM count
-  kern<<<grid, NT, smem, st>>>(s);
+  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, NT, smem, st, s));
   return 0;
 }
 
@@ -735,7 +749,7 @@ int launch_tma2(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   if (dry) return 0;
   const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
   const int grid = std::min(s.ntiles, c->num_sms * want);
-  kern<<<grid, NT, smem, st>>>(s);
+  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, NT, smem, st, s));
   return 0;
 }
 
@@ -761,7 +775,7 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
       case 0: {
         if (dry) return 0;
         int grid = std::min(o.s.nblk, c->num_sms * 8 * 4);
-        spmv_stream_kernel<<<grid, kThreads, 0, st>>>(o.s);
+        CUDA_TRY(launch_k(c->pdl != 0, spmv_stream_kernel, grid, kThreads, 0, st, o.s));
         break;
       }
       case 1: rc = launch_tma<256, 1024, 2>(c, o.s, st, dry); break;
@@ -796,12 +810,12 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
     if (dry) return 0;
     if (o.e.n == 0) return 0;
     int grid = std::min((o.e.n + kThreads - 1) / kThreads, c->num_sms * 8);
-    ew_kernel<<<grid, kThreads, 0, st>>>(o.e);
+    CUDA_TRY(launch_k(c->pdl != 0, ew_kernel, grid, kThreads, 0, st, o.e));
   } else if (o.kind == OPK_DENSE) {
     if (dry) return 0;
     const int n = c->dense_n;
     int grid = std::min((n * 32 + kThreads - 1) / kThreads, c->num_sms * 8);
-    dense_gemv_kernel<<<grid, kThreads, 0, st>>>(n, c->dense_T, o.e.a, o.e.out);
+    CUDA_TRY(launch_k(c->pdl != 0, dense_gemv_kernel, grid, kThreads, 0, st, n, (const double *)c->dense_T, (const double *)o.e.a, o.e.out));
   } else {
     return fail(7, "internal: op kind %d cannot be launched directly", o.kind);
   }
@@ -929,7 +943,7 @@ int run_program(Ctx *c, cudaStream_t st, int *nkernels) {
   std::vector<const std::vector<Op> *> P{&c->prog};
   for (int i = 0; i < n; ++i) {
     if (i == c->tail_begin && c->tail_end > c->tail_begin) {
-      tail_kernel<<<1, kTailThreads, 0, st>>>(c->d_tail, c->tail_end - c->tail_begin);
+      CUDA_TRY(launch_k(c->pdl != 0, tail_kernel, 1, kTailThreads, 0, st, (const DevOp *)c->d_tail, c->tail_end - c->tail_begin));
       CUDA_TRY(cudaGetLastError());
       ++nk;
       i = c->tail_end - 1;
@@ -1155,7 +1169,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->rank = 0; ch->nranks = 1; ch->device = c->device; ch->no_levels = NL - LA + 1;
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
-  ch->use_graph = 0; ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->dense_rows = c->dense_rows;
+  ch->use_graph = 0; ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   ch->kernel = c->kernel; ch->tile_kernel = c->tile_kernel; ch->ctas_per_sm = c->ctas_per_sm;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
@@ -2016,12 +2030,13 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
     if (!c->finalized && v != 0) c->tile_kernel = v;
   }
   else if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
+  else if (k == "pdl") c->pdl = value != 0;
   else if (k == "dbg_seq_gather") c->dbg_seq = (int)value;
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
     Ctx *ch = c->child.get();
     ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->kernel = c->kernel; ch->ctas_per_sm = c->ctas_per_sm;
-    ch->dbg_seq = c->dbg_seq; ch->dense_rows = c->dense_rows;
+    ch->dbg_seq = c->dbg_seq; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   }
   return 0;
 }

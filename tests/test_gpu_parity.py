@@ -35,11 +35,12 @@ def _device(H, **opts):
 
 
 @pytest.mark.parametrize("name", sorted(cases.CASES))
-def test_vcycle_parity(built_libs, name):
+@pytest.mark.parametrize("dense_rows", [0, 4096], ids=["sparse_all_levels", "dense_tail_default"])
+def test_vcycle_parity(built_libs, name, dense_rows):
     A, H = cases.build(name)
     b = cases.rhs(A.shape[0])
     xo = _oracle(H).apply(b)
-    d = _device(H)
+    d = _device(H, dense_rows=dense_rows)
     x = d.apply(b)
     assert cases.rel_l2(x, xo) <= TOL, name
     # repeated applies are deterministic and do not depend on leftover state
@@ -48,17 +49,18 @@ def test_vcycle_parity(built_libs, name):
     d.close()
 
 
-@pytest.mark.parametrize("opts", [dict(graph=0), dict(tail_rows=0), dict(fuse=0), dict(tail_rows=100000, tail_nnz=1e9),
-                                  dict(graph=0, fuse=0, tail_rows=0),
+@pytest.mark.parametrize("opts", [dict(graph=0), dict(dense_rows=0), dict(fuse=0, dense_rows=0), dict(pdl=0), dict(pdl=0, dense_rows=0),
+                                  dict(dense_rows=0, tail_rows=2048), dict(dense_rows=0, tail_rows=100000, tail_nnz=1e9),
+                                  dict(graph=0, fuse=0, dense_rows=0),
                                   # SpMV kernel variants: 0 = smem-staged stream kernel, 1.. = TMA-pipelined (stages / tile sizes)
-                                  dict(kernel=0, tail_rows=0), dict(kernel=1, tail_rows=0), dict(kernel=2, tail_rows=0),
-                                  dict(kernel=3, tail_rows=0), dict(kernel=4, tail_rows=0), dict(kernel=5, tail_rows=0),
-                                  dict(kernel=6, tail_rows=0), dict(kernel=7, tail_rows=0), dict(kernel=8, tail_rows=0),
-                                  dict(kernel=9, tail_rows=0), dict(kernel=10, tail_rows=0), dict(kernel=11, tail_rows=0),
-                                  dict(kernel=12, tail_rows=0), dict(kernel=13, tail_rows=0),
+                                  dict(kernel=0, dense_rows=0), dict(kernel=1, dense_rows=0), dict(kernel=2, dense_rows=0),
+                                  dict(kernel=3, dense_rows=0), dict(kernel=4, dense_rows=0), dict(kernel=5, dense_rows=0),
+                                  dict(kernel=6, dense_rows=0), dict(kernel=7, dense_rows=0), dict(kernel=8, dense_rows=0),
+                                  dict(kernel=9, dense_rows=0), dict(kernel=10, dense_rows=0), dict(kernel=11, dense_rows=0),
+                                  dict(kernel=12, dense_rows=0), dict(kernel=13, dense_rows=0),
                                   # 20..24: spmv_tma2_kernel (asynchronous cp.async gathers, fused multiply/reduce)
-                                  dict(kernel=20, tail_rows=0), dict(kernel=21, tail_rows=0), dict(kernel=22, tail_rows=0),
-                                  dict(kernel=23, tail_rows=0), dict(kernel=24, tail_rows=0),
+                                  dict(kernel=20, dense_rows=0), dict(kernel=21, dense_rows=0), dict(kernel=22, dense_rows=0),
+                                  dict(kernel=23, dense_rows=0), dict(kernel=24, dense_rows=0),
                                   dict(kernel=2, ctas_per_sm=1),
                                   # coarse levels collapsed into one dense operator (built from the same kernels at setup)
                                   dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, tail_rows=0, graph=0)],
