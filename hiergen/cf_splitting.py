@@ -29,13 +29,18 @@ def _row_reduce(ufunc, vals, indptr, empty):
     return out
 
 
-def drop_small(a, tol, relative=1, lump=False, drop_diagonal=0):
+def drop_small(a, tol, relative=1, lump=False, drop_diagonal=0, use_native=True):
     """remove_small_from_sparse (``src/PETSc_Helper.F90:207-412``).
 
     relative: 1 = tol * max|row| incl. diagonal, -1 = excl. diagonal, 0 = absolute.
     drop_diagonal: 0 never, -1 always, 1 allowed.  Entries with |v| >= row tol are kept.
     """
     a = a.tocsr()
+    if use_native:
+        from . import native
+        out = native.drop_small(a, tol, relative, lump, drop_diagonal)
+        if out is not None:
+            return out
     n = a.shape[0]
     rows = _rows_of(a)
     cols = a.indices

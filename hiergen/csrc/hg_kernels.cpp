@@ -7,6 +7,7 @@
 //                     fixed-sparsity matrix powers of
 //                     /root/reference/src/Gmres_Poly.F90:1177-1310 (row-wise, same order)
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -110,6 +111,118 @@ void hg_masked_powers(i64 n, const i64* si, const i32* sj, const double* sv, con
       }
     }
   }
+}
+
+// One-pass C = A*B: rows are processed in chunks, every chunk keeps its result until the caller
+// has allocated the output (hg_spgemm_fetch).  Same per-row arithmetic as count + fill.
+struct SpgemmResult {
+  i64 m = 0;
+  int chunk = 4096;
+  std::vector<std::vector<i32>> cols;
+  std::vector<std::vector<double>> vals;
+  std::vector<i64> rownnz;
+};
+
+void* hg_spgemm_run(i64 m, i64 ncols_b, const i64* ai, const i32* aj, const double* av, const i64* bi, const i32* bj,
+                    const double* bv, i64* total_nnz) {
+  SpgemmResult* R = new SpgemmResult();
+  R->m = m;
+  const i64 nchunk = (m + R->chunk - 1) / R->chunk;
+  R->cols.resize((size_t)nchunk); R->vals.resize((size_t)nchunk); R->rownnz.assign((size_t)m, 0);
+#pragma omp parallel
+  {
+    // sparse accumulator: dense value array + marker + list of touched columns; contributions to a
+    // column are added in encounter order (the order a stable sort by column would group them in)
+    std::vector<double> acc((size_t)std::max<i64>(ncols_b, 1), 0.0);
+    std::vector<i32> mark((size_t)std::max<i64>(ncols_b, 1), -1);
+    std::vector<i32> touched;
+#pragma omp for schedule(dynamic, 1)
+    for (i64 ch = 0; ch < nchunk; ++ch) {
+      std::vector<i32>& oc = R->cols[(size_t)ch];
+      std::vector<double>& ov = R->vals[(size_t)ch];
+      const i64 r0 = ch * R->chunk, r1 = std::min<i64>(m, r0 + R->chunk);
+      for (i64 r = r0; r < r1; ++r) {
+        touched.clear();
+        const i32 tag = (i32)r;   // unique per row: the marker never needs a reset
+        for (i64 p = ai[r]; p < ai[r + 1]; ++p) {
+          const i32 k = aj[p];
+          const double a = av[p];
+          for (i64 q = bi[k]; q < bi[k + 1]; ++q) {
+            const i32 c = bj[q];
+            if (mark[c] != tag) { mark[c] = tag; acc[c] = a * bv[q]; touched.push_back(c); }
+            else acc[c] += a * bv[q];
+          }
+        }
+        std::sort(touched.begin(), touched.end());
+        for (i32 c : touched) { oc.push_back(c); ov.push_back(acc[c]); }
+        R->rownnz[(size_t)r] = (i64)touched.size();
+      }
+    }
+  }
+  i64 tot = 0;
+  for (i64 r = 0; r < m; ++r) tot += R->rownnz[(size_t)r];
+  *total_nnz = tot;
+  return R;
+}
+
+void hg_spgemm_fetch(void* h, i64* ci, i32* cj, double* cv) {
+  SpgemmResult* R = (SpgemmResult*)h;
+  ci[0] = 0;
+  for (i64 r = 0; r < R->m; ++r) ci[r + 1] = ci[r] + R->rownnz[(size_t)r];
+  const i64 nchunk = (i64)R->cols.size();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (i64 ch = 0; ch < nchunk; ++ch) {
+    const i64 o = ci[ch * R->chunk];
+    const std::vector<i32>& oc = R->cols[(size_t)ch];
+    if (!oc.empty()) {
+      memcpy(cj + o, oc.data(), oc.size() * sizeof(i32));
+      memcpy(cv + o, R->vals[(size_t)ch].data(), oc.size() * sizeof(double));
+    }
+  }
+  delete R;
+}
+
+// remove_small_from_sparse (/root/reference/src/PETSc_Helper.F90:207-412): keep |v| >= rowtol,
+// rowtol = tol * max|row| (relative 1: incl. diagonal, -1: excl. diagonal) or tol (relative 0);
+// drop_diagonal 0 never / -1 always / 1 allowed; optional lumping of the dropped entries onto the diagonal.
+// Pass 1 (out arrays NULL) returns the kept count per row in rowcnt; pass 2 fills.
+int hg_drop_small(i64 m, const i32* ai, const i32* aj, const double* av, double tol, int relative, int lump, int drop_diagonal,
+                  i64* rowcnt, const i64* oi, i32* oj, double* ov) {
+  int bad = 0;
+#pragma omp parallel for schedule(static, 2048) reduction(| : bad)
+  for (i64 r = 0; r < m; ++r) {
+    const i64 p0 = ai[r], p1 = ai[r + 1];
+    double rowtol = tol;
+    if (relative == 1) {
+      double mx = 0.0;
+      for (i64 p = p0; p < p1; ++p) mx = std::max(mx, std::fabs(av[p]));
+      rowtol = tol * mx;
+    } else if (relative == -1) {
+      double mx = -1.0; bool any = false;
+      for (i64 p = p0; p < p1; ++p) if (aj[p] != r) { mx = std::max(mx, std::fabs(av[p])); any = true; }
+      rowtol = any ? tol * mx : -tol * 1.7976931348623157e308;
+    }
+    double lumpsum = 0.0;
+    i64 cnt = 0, dpos = -1;
+    i64 o = oi ? oi[r] : 0;
+    for (i64 p = p0; p < p1; ++p) {
+      const bool isd = aj[p] == r;
+      bool keep = std::fabs(av[p]) >= rowtol;
+      if (drop_diagonal == -1) keep = keep && !isd;
+      else if (drop_diagonal == 0) keep = keep || isd;
+      if (keep) {
+        if (oj) { oj[o] = aj[p]; ov[o] = av[p]; if (isd) dpos = o; ++o; }
+        ++cnt;
+      } else if (lump) {
+        lumpsum += av[p];
+      }
+    }
+    if (lump && oj && lumpsum != 0.0) {
+      if (dpos >= 0) ov[dpos] += lumpsum; else bad = 1;
+    }
+    if (rowcnt) rowcnt[r] = cnt;
+  }
+  return bad;
 }
 
 }  // extern "C"

@@ -56,16 +56,40 @@ def spgemm(a, b, use_native=True):
     ai, aj, av = _csr64(a)
     bi, bj, bv = _csr64(b)
     m = a.shape[0]
-    cnt = np.zeros(m, dtype=np.int64)
     i64, i32, f64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_double
-    L.hg_spgemm_count(i64(m), _p(ai, i64), _p(aj, i32), _p(bi, i64), _p(bj, i32), _p(cnt, i64))
+    L.hg_spgemm_run.restype = ctypes.c_void_p
+    tot = ctypes.c_int64(0)
+    h = L.hg_spgemm_run(i64(m), i64(b.shape[1]), _p(ai, i64), _p(aj, i32), _p(av, f64), _p(bi, i64), _p(bj, i32), _p(bv, f64), ctypes.byref(tot))
     ci = np.zeros(m + 1, dtype=np.int64)
-    np.cumsum(cnt, out=ci[1:])
-    cj = np.empty(ci[-1], dtype=np.int32)
-    cv = np.empty(ci[-1], dtype=np.float64)
-    L.hg_spgemm_fill(i64(m), _p(ai, i64), _p(aj, i32), _p(av, f64), _p(bi, i64), _p(bj, i32), _p(bv, f64),
-                     _p(ci, i64), _p(cj, i32), _p(cv, f64))
+    cj = np.empty(max(tot.value, 1), dtype=np.int32)[:tot.value]
+    cv = np.empty(max(tot.value, 1), dtype=np.float64)[:tot.value]
+    L.hg_spgemm_fetch(ctypes.c_void_p(h), _p(ci, i64), _p(cj, i32), _p(cv, f64))
     return _mk(cv, cj, ci, (a.shape[0], b.shape[1]))
+
+
+def drop_small(a, tol, relative=1, lump=False, drop_diagonal=0):
+    """Native remove_small_from_sparse; returns None when the helper library is unavailable."""
+    L = lib()
+    if L is None or a.nnz >= 2**31 - 1:
+        return None
+    a = a.tocsr()
+    ai = np.ascontiguousarray(a.indptr, dtype=np.int32)
+    aj = np.ascontiguousarray(a.indices, dtype=np.int32)
+    av = np.ascontiguousarray(a.data, dtype=np.float64)
+    m = a.shape[0]
+    i64, i32, f64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_double
+    cnt = np.zeros(m, dtype=np.int64)
+    args = (i64(m), _p(ai, i32), _p(aj, i32), _p(av, f64), ctypes.c_double(tol), ctypes.c_int(relative), ctypes.c_int(int(lump)),
+            ctypes.c_int(drop_diagonal))
+    L.hg_drop_small(*args, _p(cnt, i64), None, None, None)
+    oi = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(cnt, out=oi[1:])
+    oj = np.empty(max(oi[-1], 1), dtype=np.int32)[:oi[-1]]
+    ov = np.empty(max(oi[-1], 1), dtype=np.float64)[:oi[-1]]
+    bad = L.hg_drop_small(*args, None, _p(oi, i64), _p(oj, i32), _p(ov, f64))
+    if bad:
+        raise ValueError("lumping onto a missing diagonal")
+    return _mk(ov, oj, oi, a.shape)
 
 
 def masked_powers(S, A, coeff, sparsity_order, use_native=True):
