@@ -54,6 +54,9 @@ struct SpmvOp {
   // x += fd_m[i] * (v - fd_a[i] * x); wout[i] = x
   const double *fd_a, *fd_m; int fd_its;
   int dbg_seq;                 // measurement only: gather x sequentially instead of through col (wrong results)
+  // peer-memory ghost exchange: before the first ghost read, wait until every source rank has pushed
+  // its chunk of THIS exchange instance (ready[q] >= *epoch for the ranks q in srcmask)
+  const unsigned *gw_ready; const unsigned *gw_epoch; unsigned gw_srcmask;
 };
 
 // out[i] (=|+=) alpha * a[i] * (b ? b[i] : 1) / (dv ? dv[i] : 1)
@@ -79,11 +82,30 @@ struct DevOp {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- system-scope flags of the peer-memory ghost exchange (written by one GPU, polled by another)
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// consumer side: called by ONE thread of a CTA before the CTA's first ghost read
+__device__ __forceinline__ void ghost_wait(const unsigned *ready, const unsigned *epoch, unsigned srcmask) {
+  if (!ready) return;
+  const unsigned e = *epoch;
+  for (unsigned m = srcmask; m; m &= m - 1) {
+    const int q = __ffs(m) - 1;
+    while ((int)(ld_acquire_sys(ready + q) - e) < 0) __nanosleep(20);
+  }
+}
+
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
 __device__ __forceinline__ double gather_x(const SpmvOp &op, int c) {
-  if (op.xg != nullptr && c >= op.nloc) return op.xg[c - op.nloc];
+  if (op.xg != nullptr && c >= op.nloc) return __ldcg(op.xg + (c - op.nloc));  // ghosts: written by peers, read through L2
   return op.x[c];
 }
 
@@ -181,6 +203,8 @@ __global__ void __launch_bounds__(kThreads) spmv_stream_kernel(const SpmvOp op) 
   pdl_wait();
   __shared__ double prod[kTile];
   __shared__ double red[kThreads / 32];
+  if (threadIdx.x == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+  __syncthreads();
   for (int b = blockIdx.x; b < op.nblk; b += gridDim.x) process_block<kThreads>(op, b, prod, red);
 }
 
@@ -291,6 +315,7 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
     for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);   // matrix data only: legal before pdl_wait
   }
   pdl_wait();   // from here on the vectors written by the previous kernels are read
+  if (tid == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);   // peers' pushes (the local tiles are already in flight)
   __syncthreads();
 
   for (int it = 0; it < my_tiles; ++it) {
@@ -483,6 +508,7 @@ __global__ void __launch_bounds__(NT) spmv_tma2_kernel(const SpmvOp op) {
     for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);
   }
   pdl_wait();
+  if (tid == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
   __syncthreads();
   if (my_tiles > 0) stage_gathers(0);
 
@@ -583,6 +609,68 @@ __global__ void unit_vector_kernel(int n, int j, double *v) {
 }
 __global__ void store_column_kernel(int n, int j, const double *v, double *T) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) T[(size_t)i * n + j] = v[i];
+}
+
+// ---- peer-memory ghost exchange (one process per GPU with IPC-mapped arenas, or an in-process group)
+struct PushOp {
+  int n;                        // entries to push
+  const int *idx;               // positions in x
+  const double *x;
+  int nranks, me;
+  const int *send_off;          // [nranks + 1] prefix of send counts
+  const unsigned long long *dst;        // [nranks] address (in MY address space) of my chunk inside peer p's ghost buffer
+  const unsigned long long *peer_flags; // [nranks] address of peer p's flag block
+  unsigned *my_flags;           // my own flag block (acks are written here by the consumers)
+  const unsigned *epoch;
+  unsigned *done;               // CTA counter of this instance
+  int inst, ack_inst, ack_delta, max_inst;
+  unsigned dstmask;
+};
+// flag block layout: [0..63] header (epoch at word 0), ready[max_inst][32], ack[max_inst][32]
+__device__ __forceinline__ size_t flag_ready(int inst, int q) { return 64 + (size_t)inst * 32 + q; }
+__device__ __forceinline__ size_t flag_ack(int max_inst, int inst, int q) { return 64 + (size_t)max_inst * 32 + (size_t)inst * 32 + q; }
+
+__global__ void epoch_kernel(unsigned *epoch) { *epoch += 1; }
+
+__global__ void __launch_bounds__(kThreads) push_kernel(const PushOp o) {
+  const unsigned e = *o.epoch;
+  if (threadIdx.x == 0 && o.ack_inst >= 0) {
+    // the consumers must have finished reading the previous contents of their ghost buffer
+    for (unsigned m = o.dstmask; m; m &= m - 1) {
+      const int p = __ffs(m) - 1;
+      const unsigned *ack = o.my_flags + flag_ack(o.max_inst, o.ack_inst, p);
+      while ((int)(ld_acquire_sys(ack) - (e - (unsigned)o.ack_delta)) < 0) __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < o.n; j += gridDim.x * blockDim.x) {
+    int p = 0;
+    while (j >= o.send_off[p + 1]) ++p;
+    double *dst = reinterpret_cast<double *>(o.dst[p]) + (j - o.send_off[p]);
+    *dst = o.x[o.idx[j]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(o.done, 1u);
+    if (prev == gridDim.x - 1) {   // last CTA: every chunk is written and fenced -> raise the flags
+      *o.done = 0;
+      __threadfence_system();
+      for (unsigned m = o.dstmask; m; m &= m - 1) {
+        const int p = __ffs(m) - 1;
+        st_release_sys(reinterpret_cast<unsigned *>(o.peer_flags[p]) + flag_ready(o.inst, o.me), e);
+      }
+    }
+  }
+}
+
+// consumer -> producers: "I have finished reading the ghosts of instance inst" (runs after the SpMV)
+__global__ void ack_kernel(const unsigned long long *peer_flags, const unsigned *epoch, int max_inst, int inst, int me, unsigned srcmask) {
+  const unsigned e = *epoch;
+  for (unsigned m = srcmask; m; m &= m - 1) {
+    const int q = __ffs(m) - 1;
+    st_release_sys(reinterpret_cast<unsigned *>(peer_flags[q]) + flag_ack(max_inst, inst, me), e);
+  }
 }
 
 // Single-CTA "tail": runs a whole list of ops (the small coarse levels: restrictions, coarse

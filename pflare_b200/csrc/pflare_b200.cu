@@ -99,6 +99,12 @@ struct DevPlan {
   int *d_send_idx = nullptr;
   double *d_sendbuf = nullptr;
   double *d_xg = nullptr;
+  // peer-memory exchange
+  int64_t xg_off = 0;                        // byte offset of d_xg inside this rank's arena
+  int *d_send_off = nullptr;                 // [P + 1]
+  unsigned long long *d_dst = nullptr;       // [P] where my chunk goes inside peer p's ghost buffer (my address space)
+  unsigned dstmask = 0, srcmask = 0;
+  int first_inst = -1, last_inst = -1;       // exchange instances of this plan inside the cycle program
 };
 
 struct DevCSR {
@@ -149,14 +155,16 @@ struct Level {
   bool any_c = false;
 };
 
-enum { OPK_SPMV = 0, OPK_EW = 1, OPK_XCHG = 2, OPK_GATHER0 = 3, OPK_SCATTER0 = 4, OPK_CHILD = 5, OPK_DENSE = 6 };
+enum { OPK_SPMV = 0, OPK_EW = 1, OPK_XCHG = 2, OPK_GATHER0 = 3, OPK_SCATTER0 = 4, OPK_CHILD = 5, OPK_DENSE = 6, OPK_EPOCH = 7, OPK_ACK = 8 };
+const int kMaxInst = 4096;   // exchange instances per cycle the flag block has room for
 
 struct Op {
   int kind = OPK_SPMV;
   SpmvOp s{};
   EwOp e{};
-  DevPlan *xp = nullptr;        // OPK_XCHG: which plan; xsrc = the vector segment being exchanged
+  DevPlan *xp = nullptr;        // OPK_XCHG / OPK_ACK: which plan; xsrc = the vector segment being exchanged
   const double *xsrc = nullptr;
+  int inst = -1, ack_inst = -1, ack_delta = 0;   // peer-memory exchange instance (and the one whose acks it waits for)
   int level = 0;
   int tag = 0;  // 1 restrict, 2 coarse, 3 A_fc(+W), 4 A_ff residual, 5 inverse, 6 elementwise, 7 fused local smooth, 8 A_cf, 9 A_cc, 10 exchange, 11 dense tail
   double bytes = 0, nnz = 0;
@@ -214,6 +222,16 @@ struct Ctx {
   std::unique_ptr<Ctx> child;            // rank 0: serial hierarchy of the agglomerated levels
   double *child_b = nullptr, *child_x = nullptr;  // rank 0: global natural vectors of level l_agg
   double ghost_bytes = 0; int xchg_groups = 0;
+  // peer-memory ghost exchange (option p2p): one arena per rank = [flag block | ghost buffers], mapped by every peer
+  int p2p = 1;
+  bool p2p_ready = false;
+  char *arena = nullptr; size_t arena_bytes = 0;
+  std::vector<void *> peer_arena;        // [P] peers' arenas in my address space (IPC-mapped or same process)
+  std::vector<bool> peer_ipc;
+  unsigned long long *d_peer_flags = nullptr;  // [P]
+  unsigned *d_done = nullptr;            // [kMaxInst] CTA counters of the push kernels
+  int n_inst = 0;
+  unsigned *flags() const { return reinterpret_cast<unsigned *>(arena); }
 };
 
 template <class T>
@@ -379,6 +397,7 @@ struct Builder {
   Ctx *c;
   std::vector<Op> *out;
   int level = 0;
+  bool use_p2p = false;   // only the cycle program owns exchange instances; ad-hoc op lists go through NCCL / copies
 
   SpmvOp base(const DevCSR &A, const double *x) {
     SpmvOp s{};
@@ -389,17 +408,37 @@ struct Builder {
     return s;
   }
   void push_spmv(const SpmvOp &s, const DevCSR &A, int tag, int aux_reads, int w, double extra_bytes = 0) {
-    if (A.xp && A.xp->global_any) {  // ghost scatter of MatMult_MPIAIJ: pack + point-to-point exchange of s.x
+    const bool xchg = A.xp && A.xp->global_any;
+    const bool p2p = xchg && c->p2p_ready && use_p2p;
+    int inst = -1;
+    if (xchg) {  // ghost scatter of MatMult_MPIAIJ: pack + point-to-point exchange of s.x
       Op x;
       x.kind = OPK_XCHG; x.xp = A.xp; x.xsrc = s.x; x.level = level; x.tag = 10;
       x.bytes = 8.0 * (A.xp->plan.n_ghost + A.xp->plan.n_send());
+      if (p2p) {
+        inst = c->n_inst++;
+        x.inst = inst;
+        x.ack_inst = A.xp->last_inst; x.ack_delta = 0;        // same cycle; the first instance is fixed up at the end
+        if (A.xp->first_inst < 0) A.xp->first_inst = inst;
+        A.xp->last_inst = inst;
+      }
       out->push_back(x);
     }
     Op o;
     o.kind = OPK_SPMV; o.s = s; o.level = level; o.tag = tag;
     o.bytes = spmv_bytes(A, aux_reads, w) + extra_bytes;
     o.nnz = (double)(A.nnz_model >= 0 ? A.nnz_model : A.nnz);
+    if (p2p) {
+      o.s.gw_ready = c->flags() + 64 + (size_t)inst * 32;
+      o.s.gw_epoch = c->flags();
+      o.s.gw_srcmask = A.xp->srcmask;
+    }
     out->push_back(o);
+    if (p2p) {   // tell the producers that this rank is done with the ghosts of this instance
+      Op a;
+      a.kind = OPK_ACK; a.xp = A.xp; a.inst = inst; a.level = level; a.tag = 10;
+      out->push_back(a);
+    }
   }
   // out (=|+=) alpha * a .* b ./ dv
   void push_ew(int n, const double *a, const double *b, const double *dv, double alpha, double *dst, int mode,
@@ -860,6 +899,33 @@ int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op
         int rc = launch_op(R[r], o, st);
         if (rc) return rc;
       }
+    } else if (kind == OPK_EPOCH) {
+      for (int r = 0; r < nr; ++r) epoch_kernel<<<1, 1, 0, st>>>(R[r]->flags());
+      CUDA_TRY(cudaGetLastError());
+    } else if (kind == OPK_ACK) {
+      for (int r = 0; r < nr; ++r) {
+        const Op &o = (*progs[r])[i];
+        if (!o.xp->srcmask) continue;
+        ack_kernel<<<1, 1, 0, st>>>(R[r]->d_peer_flags, R[r]->flags(), kMaxInst, o.inst, R[r]->rank, o.xp->srcmask);
+      }
+      CUDA_TRY(cudaGetLastError());
+    } else if (kind == OPK_XCHG && (*progs[0])[i].inst >= 0) {
+      // peer-memory exchange: every rank pushes its chunks straight into the consumers' ghost buffers and
+      // raises their flags; the consumers' SpMV kernels wait on the flags (kernels.cuh: push_kernel / ghost_wait)
+      for (int r = 0; r < nr; ++r) {
+        Ctx *c = R[r];
+        const Op &o = (*progs[r])[i];
+        const DevPlan *D = o.xp;
+        if (!D->dstmask) continue;
+        PushOp po;
+        po.n = D->plan.n_send(); po.idx = D->d_send_idx; po.x = o.xsrc; po.nranks = c->nranks; po.me = c->rank;
+        po.send_off = D->d_send_off; po.dst = D->d_dst; po.peer_flags = c->d_peer_flags; po.my_flags = c->flags();
+        po.epoch = c->flags(); po.done = c->d_done + o.inst; po.inst = o.inst; po.ack_inst = o.ack_inst; po.ack_delta = o.ack_delta;
+        po.max_inst = kMaxInst; po.dstmask = D->dstmask;
+        const int grid = std::max(1, std::min((po.n + kThreads - 1) / kThreads, 64));
+        push_kernel<<<grid, kThreads, 0, st>>>(po);
+      }
+      CUDA_TRY(cudaGetLastError());
     } else if (kind == OPK_XCHG) {
       for (int r = 0; r < nr; ++r) {
         int rc = launch_pack(R[r], (*progs[r])[i], st);
@@ -987,6 +1053,10 @@ int build_program(Ctx *c) {
   const bool agg = c->l_agg <= NL;
   const int LB = agg ? c->l_agg : NL;  // bottom level of this context's nested vectors
   Builder B{c, &c->prog};
+  B.use_p2p = true;
+  c->n_inst = 0;
+  for (DevPlan &D : c->plans) D.first_inst = D.last_inst = -1;
+  if (c->p2p_ready) { Op e; e.kind = OPK_EPOCH; e.tag = 10; c->prog.push_back(e); }
   // which levels go to the single-CTA tail: the longest suffix of small levels (serial contexts only)
   int ltail = NL + 1;
   if (c->nranks == 1) {
@@ -1069,6 +1139,12 @@ int build_program(Ctx *c) {
   } else {
     c->tail_begin = c->tail_end = -1;
     c->tail_levels = 0;
+  }
+  if (c->p2p_ready) {
+    if (c->n_inst > kMaxInst) return fail(25, "the cycle needs %d ghost exchanges, the flag block holds %d: set option p2p=0", c->n_inst, kMaxInst);
+    // the first exchange of a plan in a cycle reuses the ghost buffer of its LAST exchange of the previous cycle
+    for (Op &o : c->prog)
+      if (o.kind == OPK_XCHG && o.inst >= 0 && o.ack_inst < 0) { o.ack_inst = o.xp->last_inst; o.ack_delta = 1; }
   }
   c->ghost_bytes = 0; c->xchg_groups = 0;
   for (const Op &o : c->prog)
@@ -1256,6 +1332,67 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
     }
   }
   return finalize_ctx(ch);
+}
+
+// Map every peer's arena and tell every producer where its chunks go (X4).  One process per GPU: CUDA IPC
+// handles; in-process rank group: the raw pointers.
+int setup_p2p(Ctx *c) {
+  const int P = c->nranks;
+  int rc;
+  struct Hello { int32_t same_process_tag; int32_t pad; uint64_t raw; cudaIpcMemHandle_t ipc; };
+  Hello me{};
+  me.same_process_tag = c->cluster ? 1 : 0;
+  me.raw = (uint64_t)(uintptr_t)c->arena;
+  if (!c->cluster) CUDA_TRY(cudaIpcGetMemHandle(&me.ipc, c->arena));
+  std::vector<std::vector<char>> out((size_t)P), in;
+  for (int p = 0; p < P; ++p) {
+    Writer w;
+    w.put(me);
+    for (DevPlan &D : c->plans) w.put<int64_t>(D.xg_off + 8 * (int64_t)D.plan.recv_off[p]);   // where p's chunk lands in MY arena
+    out[p] = std::move(w.buf);
+  }
+  std::string err;
+  if (exchange_blobs(c->hostcomm.get(), out, &in, &err)) return fail(22, "peer-memory setup exchange failed: %s", err.c_str());
+  c->peer_arena.assign((size_t)P, nullptr);
+  c->peer_ipc.assign((size_t)P, false);
+  std::vector<unsigned long long> pf((size_t)P, 0);
+  std::vector<std::vector<int64_t>> dst_off((size_t)P);
+  for (int p = 0; p < P; ++p) {
+    Reader r(in[p]);
+    const Hello h = r.get<Hello>();
+    for (size_t k = 0; k < c->plans.size(); ++k) dst_off[p].push_back(r.get<int64_t>());
+    if (!r.ok) return fail(24, "malformed peer-memory hello from rank %d", p);
+    if (p == c->rank) c->peer_arena[p] = c->arena;
+    else if (h.same_process_tag) c->peer_arena[p] = (void *)(uintptr_t)h.raw;
+    else {
+      void *ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(26, "cudaIpcOpenMemHandle(rank %d): %s -- set option p2p=0 to use NCCL", p, cudaGetErrorString(e));
+      c->peer_arena[p] = ptr; c->peer_ipc[p] = true;
+    }
+    pf[p] = (unsigned long long)(uintptr_t)c->peer_arena[p];
+  }
+  if ((rc = dev_upload(c, &c->d_peer_flags, pf))) return rc;
+  if ((rc = dev_alloc(c, &c->d_done, (size_t)kMaxInst))) return rc;
+  CUDA_TRY(cudaMemset(c->d_done, 0, kMaxInst * sizeof(unsigned)));
+  size_t k = 0;
+  for (DevPlan &D : c->plans) {
+    std::vector<int> so((size_t)P + 1, 0);
+    std::vector<unsigned long long> dst((size_t)P, 0);
+    for (int p = 0; p < P; ++p) {
+      so[p] = D.plan.send_off[p];
+      dst[p] = pf[p] + (unsigned long long)dst_off[p][k];
+    }
+    // send_off[] is only meaningful for peers with a non-zero count: rebuild it as a proper prefix
+    int acc = 0;
+    for (int p = 0; p < P; ++p) { so[p] = acc; acc += D.plan.send_count[p]; }
+    so[P] = acc;
+    if ((rc = dev_upload(c, &D.d_send_off, so))) return rc;
+    if ((rc = dev_upload(c, &D.d_dst, dst))) return rc;
+    ++k;
+  }
+  c->p2p_ready = true;
+  return 0;
 }
 
 // ------------------------------------------------------------------ setup: the layout
@@ -1560,12 +1697,28 @@ int finalize_ctx(Ctx *c) {
       }
       if (!r.ok) return fail(24, "truncated ghost request from rank %d", q);
     }
-    if (c->device >= 0)
+    for (DevPlan &D : c->plans)
+      for (int q = 0; q < P; ++q) {
+        if (D.plan.send_count[q]) D.dstmask |= 1u << q;
+        if (D.plan.recv_count[q]) D.srcmask |= 1u << q;
+      }
+    if (c->device >= 0) {
+      // one arena per rank: [flag block | ghost buffers of every operator]; peers map it (peer-memory exchange)
+      const size_t flag_bytes = (64 + 2 * (size_t)kMaxInst * 32) * sizeof(unsigned);
+      size_t off = (flag_bytes + 255) & ~(size_t)255;
+      for (DevPlan &D : c->plans) { D.xg_off = (int64_t)off; off += (((size_t)D.plan.n_ghost * 8) + 255) & ~(size_t)255; }
+      c->arena_bytes = off;
+      if ((rc = dev_alloc(c, &c->arena, c->arena_bytes))) return rc;
+      CUDA_TRY(cudaMemset(c->arena, 0, c->arena_bytes));
       for (DevPlan &D : c->plans) {
         if ((rc = dev_upload(c, &D.d_send_idx, D.plan.send_idx))) return rc;
         if ((rc = dev_alloc(c, &D.d_sendbuf, (size_t)D.plan.n_send()))) return rc;
-        if ((rc = dev_alloc(c, &D.d_xg, (size_t)D.plan.n_ghost))) return rc;
+        D.d_xg = reinterpret_cast<double *>(c->arena + D.xg_off);
       }
+      if (c->p2p && P <= 32) {
+        if ((rc = setup_p2p(c))) return rc;
+      }
+    }
   }
   c->planned = true;
   if (c->device < 0) {  // host-only planning context: the program is still built (op list, counters), nothing runs
@@ -2031,6 +2184,10 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   }
   else if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
   else if (k == "pdl") c->pdl = value != 0;
+  else if (k == "p2p") {
+    if (c->finalized || c->planned) return fail(2, "p2p must be set before finalize_setup");
+    c->p2p = value != 0;
+  }
   else if (k == "dbg_seq_gather") c->dbg_seq = (int)value;
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
@@ -2068,6 +2225,8 @@ static void destroy_ctx(Ctx *c) {
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->graph) cudaGraphDestroy(c->graph);
     if (c->child) { destroy_ctx(c->child.release()); }
+    for (size_t p = 0; p < c->peer_arena.size(); ++p)
+      if (c->peer_ipc[p] && c->peer_arena[p]) cudaIpcCloseMemHandle(c->peer_arena[p]);
     for (void *p : c->allocs) cudaFree(p);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
   }

@@ -51,13 +51,28 @@ def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
         assert all(s["exchange_groups"] > 0 for s in stats)
 
 
-@pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=5), dict(dense_rows=0), dict(pdl=0)], ids=str)
+@pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=5), dict(dense_rows=0), dict(pdl=0), dict(p2p=0), dict(p2p=0, graph=0)], ids=str)
 def test_partitioned_execution_modes(built_libs, opts):
     A, H = cases.build("fd2d_64")
     b = cases.rhs(A.shape[0], seed=3)
     xo = _oracle(H).apply(b)
     x, _ = _cluster_apply(H, 3, b, agg_rows=300, **opts)
     assert cases.rel_l2(x, xo) <= TOL
+
+
+def test_repeated_applies_reuse_ghost_buffers_safely(built_libs):
+    """The peer-memory exchange reuses every ghost buffer across exchanges and cycles (epoch flags + acks)."""
+    A, H = cases.build("fd2d_mf_newton")      # matrix-free Newton smoothing: the A_ff plan is exchanged many times per cycle
+    parts = hiergen.partition(H, 4)
+    cl = pflare_b200.ClusterAIR(H.no_levels, 4)
+    cl.set_option("agg_rows", 300)
+    cl.upload(parts)
+    O = _oracle(H)
+    for seed in range(5):
+        b = cases.rhs(A.shape[0], seed=seed)
+        xs = cl.apply(hiergen.scatter_vector(b, parts[0].rangesV[0]))
+        assert cases.rel_l2(np.concatenate(xs), O.apply(b)) <= TOL
+    cl.close()
 
 
 def test_more_ranks_than_coarse_rows(built_libs):
