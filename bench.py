@@ -292,6 +292,17 @@ def run_gpu(args):
             ms = float(tt.item())
         return ms / steps
 
+    if args.profile_one_cycle:
+        for _ in range(args.warmup):
+            dev.apply_ptr(b.data_ptr(), x.data_ptr(), 1)
+        dev.synchronize()
+        torch.cuda.profiler.start()
+        dev.apply_ptr(b.data_ptr(), x.data_ptr(), 1)
+        dev.synchronize()
+        torch.cuda.profiler.stop()
+        log("[bench] profiled one V-cycle")
+        pc.destroy()
+        return
     # device-resident leg
     with ClockSampler(local) as clk:
         ms_dev = timed(lambda: dev.apply_ptr(b.data_ptr(), x.data_ptr(), 1), args.steps, args.warmup)
@@ -346,8 +357,8 @@ def run_gpu(args):
     achieved = tot_by / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
     roof = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "kernel": "spmv_stream_kernel", "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650",
-        "how": "sum of algorithmic bytes of all spmv_stream_kernel launches of one V-cycle / sum of their CUDA-event durations (launch by launch, graph off)",
+        "kernel": "spmv_tma_kernel<256,1024,2> (TMA-pipelined CSR SpMV mega-op)", "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650",
+        "how": "sum of algorithmic bytes of all SpMV-kernel launches of one V-cycle / sum of their CUDA-event durations (launch by launch, graph off)",
         "cycle_achieved": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9,      # this rank's bytes / the cycle time
         "cycle_frac": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9 / peak,
         "largest_launch": {"bytes": biggest[0], "ms": biggest[1], "level": biggest[2],
@@ -377,7 +388,7 @@ def run_gpu(args):
             "config": {"workload": name, "rows": n, "levels": H.no_levels, "nnz_level1": int(A.nnz),
                        "l2": "inputs larger than L2: %.2f GB of operators streamed per cycle (whole job), no flush" % (job_bytes / 1e9),
                        "device_bytes": job_dev, "rhs": "seeded uniform(0,1), seed 1234",
-                       "partition": "1 GPU" if world == 1 else "%d ranks, contiguous row blocks (PETSc MPIAIJ ownership), ghost exchange = NCCL send/recv, levels >= %d agglomerated on rank 0" % (world, l_agg),
+                       "partition": "1 GPU" if world == 1 else "%d ranks, contiguous row blocks (PETSc MPIAIJ ownership), ghost exchange = %s, levels >= %d agglomerated on rank 0" % (world, "peer-memory push (CUDA IPC)" if any(o.startswith("p2p=1") for o in args.opt) else "NCCL send/recv", l_agg),
                        "ghost_bytes_per_cycle": job_ghost, "exchange_groups_per_cycle_rank0": int(st["exchange_groups"]),
                        "library_options": args.opt},
             "roofline": roof, "cpu_baseline": cpu,
@@ -408,6 +419,8 @@ def main():
     ap.add_argument("--no-cache", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")
     ap.add_argument("--compare-opt", action="append", default=[], help="after the main run, re-time the device-resident leg with this option changed (key=value)")
+    ap.add_argument("--profile-one-cycle", action="store_true",
+                    help="bracket exactly one V-cycle with cudaProfilerStart/Stop (run under `ncu --profile-from-start off`) and exit")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch table of one V-cycle (CUDA events) to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

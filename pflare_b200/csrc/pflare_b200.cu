@@ -223,7 +223,7 @@ struct Ctx {
   double *child_b = nullptr, *child_x = nullptr;  // rank 0: global natural vectors of level l_agg
   double ghost_bytes = 0; int xchg_groups = 0;
   // peer-memory ghost exchange (option p2p): one arena per rank = [flag block | ghost buffers], mapped by every peer
-  int p2p = 1;
+  int p2p = 0;   // 1: peer-memory push/flag exchange (CUDA IPC); 0: NCCL send/recv (measured faster in round 1)
   bool p2p_ready = false;
   char *arena = nullptr; size_t arena_bytes = 0;
   std::vector<void *> peer_arena;        // [P] peers' arenas in my address space (IPC-mapped or same process)
@@ -461,6 +461,7 @@ struct Builder {
     }
     if (I.kind == 2) {
       push_ew(n, src, I.ddiag, nullptr, 1.0, dst, mode);
+      out->back().nnz = (double)n;   // the reference's work model counts a MATDIAGONAL MatMult as n nonzeros
       return 0;
     }
     if (I.kind != 3) return fail(4, "level %d: approximate inverse not set", level);
@@ -583,6 +584,7 @@ struct Builder {
         s.fd_a = Lv.aff_diag; s.fd_m = Lv.inv_ff.ddiag; s.fd_its = its;
         extra += 16.0 * Lv.nf;
         push_spmv(s, A, 7, 1, 0, extra);
+        out->back().nnz += 2.0 * its * Lv.nf;   // the its x (diagonal A_ff + diagonal M_ff) products folded into this op
         return 0;
       }
       s.out = S[0]; s.out_mode = 1;

@@ -115,6 +115,33 @@ def _products_with_lookup(H, parts, rank, world, cl, l_agg):
 _PACKS = {}
 
 
+def test_work_model_matches_reference_nnz_count(built_libs):
+    """pflare_b200_get_stats[2] == nnzs_air_v of src/AIR_MG_Stats.F90:79-252 minus the identity blocks of R and P
+    (never stored here); checked on a host-only planning context."""
+    for name in ("fd2d_64", "fd2d_mf_arnoldi", "fd2d_fcf", "fd2d_jacobi"):
+        A, H = cases.build(name)
+        tot = 0
+        for lv in H.levels:
+            for s in lv.smooth_order:
+                if s == 0:
+                    break
+                its = abs(s)
+                inv, Ad, Aoff = (lv.inv_A_ff, lv.A_ff, lv.A_fc) if s > 0 else (lv.inv_A_cc, lv.A_cc, lv.A_cf)
+                if inv.kind == "poly":
+                    co = np.asarray(inv.coeffs)
+                    ninv = int(np.count_nonzero(co[:-1, 0])) * Ad.nnz         # Horner: one product per non-zero lower coefficient
+                else:
+                    ninv = inv.nnz()
+                tot += its * (ninv + Ad.nnz) + Aoff.nnz
+            tot += (lv.R.nnz - lv.is_coarse.size) + (lv.P.nnz - lv.is_coarse.size)
+        tot += H.inv_coarse.nnz()
+        cl = pflare_b200.ClusterAIR(H.no_levels, 1, device=-1)
+        hiergen.feed(H, cl.ranks[0])
+        cl.finalize()
+        assert cl.ranks[0].stats()["nnz_per_cycle"] == tot, name
+        cl.close()
+
+
 def test_gloo_two_processes(built_libs):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_gloo_check.py")]
