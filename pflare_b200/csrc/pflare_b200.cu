@@ -2140,23 +2140,29 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
   if (!c->finalized || c->no_levels < 2 || c->cluster) return fail(6, "profile_apply needs a finalized stand-alone hierarchy with >= 2 levels");
   Level &L1 = c->L[1];
   const int n = (int)c->prog.size();
-  std::vector<cudaEvent_t> ev((size_t)n + 1);
+  std::vector<cudaEvent_t> ev((size_t)n + 3);
   for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
-  if ((rc = launch_ew_now(c, L1.n, b_dev, c->bb, L1.d_inv, nullptr, c->stream))) return rc;
   CUDA_TRY(cudaEventRecord(ev[0], c->stream));
+  if ((rc = launch_ew_now(c, L1.n, b_dev, c->bb, L1.d_inv, nullptr, c->stream))) return rc;   // entry permutation
+  CUDA_TRY(cudaEventRecord(ev[1], c->stream));
   std::vector<Ctx *> R{c};
   std::vector<const std::vector<Op> *> Pp{&c->prog};
   for (int i = 0; i < n; ++i) {
     if ((rc = exec_ops(R, Pp, i, i + 1, c->stream))) return rc;
-    CUDA_TRY(cudaEventRecord(ev[(size_t)i + 1], c->stream));
+    CUDA_TRY(cudaEventRecord(ev[(size_t)i + 2], c->stream));
   }
-  if ((rc = launch_ew_now(c, L1.n, c->xb, x_dev, L1.d_pos, nullptr, c->stream))) return rc;
+  if ((rc = launch_ew_now(c, L1.n, c->xb, x_dev, L1.d_pos, nullptr, c->stream))) return rc;   // exit permutation
+  CUDA_TRY(cudaEventRecord(ev[(size_t)n + 2], c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   int cnt = 0;
-  for (int i = 0; i < n && cnt < max_ops; ++i) {
+  for (int i = -1; i <= n && cnt < max_ops; ++i) {
     float t = 0;
-    CUDA_TRY(cudaEventElapsedTime(&t, ev[i], ev[(size_t)i + 1]));
-    ms[cnt] = t; bytes[cnt] = c->prog[i].bytes; level[cnt] = c->prog[i].level; kind[cnt] = c->prog[i].tag;
+    CUDA_TRY(cudaEventElapsedTime(&t, ev[(size_t)(i + 1)], ev[(size_t)(i + 2)]));
+    const bool perm = i < 0 || i == n;
+    ms[cnt] = t;
+    bytes[cnt] = perm ? 20.0 * L1.n : c->prog[i].bytes;
+    level[cnt] = perm ? 1 : c->prog[i].level;
+    kind[cnt] = perm ? 6 : c->prog[i].tag;
     ++cnt;
   }
   *n_ops = cnt;
