@@ -265,8 +265,10 @@ struct TmaStage {
   int rp[MAXROWS + 8];
 };
 
-template <int NT, int TILE, int STAGES, bool ROWMAP, int MINB>
+template <int NT, int TILE, int STAGES, int MODE, int MINB>   // MODE 0: serial row sums, 1: row-mapped multiply, 2: g-lane row sums
 __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
+  constexpr bool ROWMAP = MODE == 1;
+  constexpr bool GRED = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef TmaStage<TILE, NT> Stage;
   Stage *stages = reinterpret_cast<Stage *>(smem_raw);
@@ -329,12 +331,12 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
     if (d.n <= TILE) {
       // operands of my row's epilogue: in flight while the tile lands and is multiplied
       int g = 1;
-      if (ROWMAP) {
+      if (ROWMAP || GRED) {
         while (g < 32 && d.nrows * (g << 1) <= NT) g <<= 1;
       }
-      const bool has_row = ROWMAP ? (tid < d.nrows * g && (tid & (g - 1)) == 0) : (tid < d.nrows);
+      const bool has_row = (ROWMAP || GRED) ? (tid < d.nrows * g && (tid & (g - 1)) == 0) : (tid < d.nrows);
       EpiPre pre;
-      if (has_row && op.dbg_seq != 2 && op.dbg_seq != 5) pre = epi_prefetch(op, d.r0 + (ROWMAP ? tid / g : tid));
+      if (has_row && op.dbg_seq != 2 && op.dbg_seq != 5) pre = epi_prefetch(op, d.r0 + ((ROWMAP || GRED) ? tid / g : tid));
       mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
       const int o = d.s & 3;
       if (op.dbg_seq == 2) {  // measurement only: TMA stream + barriers, no work
@@ -385,7 +387,24 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
           if (k < d.n) S.val[o + k] = S.val[o + k] * xr[k0];
         }
         __syncthreads();
-        if (has_row) {
+        if (GRED) {
+          // g lanes per row read the row's products at consecutive addresses (few bank conflicts) and
+          // shuffle-reduce; the lane-0 thread of a group owns the row's epilogue
+          const bool active = tid < d.nrows * g;
+          const int row = tid / g, lg = tid & (g - 1);
+          int p = 0, q = 0;
+          if (active) {
+            const int ro = d.r0 & 3;
+            p = S.rp[ro + row] - d.s + o;
+            q = S.rp[ro + row + 1] - d.s + o;
+          }
+          double xw = 0.0;
+          if (op.wlast && active) { --q; xw = S.val[q]; }
+          double sum = 0.0;
+          for (int k = p + lg; k < q; k += g) sum += S.val[k];
+          for (int w = g >> 1; w > 0; w >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, w, g);
+          if (has_row) epi_finish(op, d.r0 + row, sum, xw, pre);
+        } else if (has_row) {
           const int ro = d.r0 & 3;
           int p = S.rp[ro + tid] - d.s + o;
           int q = S.rp[ro + tid + 1] - d.s + o;

@@ -68,7 +68,8 @@ struct Variant { int nt, tile, stages; };
 const Variant kVariants[] = {{0, 0, 0}, {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {256, 2048, 3}, {512, 2048, 2}, {512, 4096, 2}, {128, 512, 3}, {128, 1024, 4},
                              {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {512, 2048, 2}, {128, 512, 3},   // 9..13: row-mapped multiply
                              {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 3}, {128, 512, 2}, {128, 512, 3},  // 14..19: register-capped for more resident CTAs
-                             {256, 1024, 3}, {256, 1024, 4}, {256, 2048, 3}, {512, 2048, 3}, {128, 512, 4}};  // 20..24: asynchronous gathers (spmv_tma2_kernel)
+                             {256, 1024, 3}, {256, 1024, 4}, {256, 2048, 3}, {512, 2048, 3}, {128, 512, 4},  // 20..24: asynchronous gathers (spmv_tma2_kernel)
+                             {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {512, 2048, 2}};  // 25..28: nnz-mapped multiply + g-lane row sums
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
 struct HostCSR {
@@ -758,9 +759,9 @@ cudaError_t launch_k(bool pdl, K kern, int grid, int block, size_t smem, cudaStr
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
-template <int NT, int TILE, int STAGES, bool ROWMAP = false, int MINB = 1>
+template <int NT, int TILE, int STAGES, int MODE = 0, int MINB = 1>
 int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_tma_kernel<NT, TILE, STAGES, ROWMAP, MINB>;
+  auto kern = spmv_tma_kernel<NT, TILE, STAGES, MODE, MINB>;
   const size_t smem = sizeof(TmaStage<TILE, NT>) * STAGES;
   static int per_sm = 0;   // resident CTAs per SM of this instantiation (occupancy calculator, once)
   if (per_sm == 0) {
@@ -827,22 +828,26 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
       case 6: rc = launch_tma<512, 4096, 2>(c, o.s, st, dry); break;
       case 7: rc = launch_tma<128, 512, 3>(c, o.s, st, dry); break;
       case 8: rc = launch_tma<128, 1024, 4>(c, o.s, st, dry); break;
-      case 9: rc = launch_tma<256, 1024, 2, true>(c, o.s, st, dry); break;
-      case 10: rc = launch_tma<256, 1024, 3, true>(c, o.s, st, dry); break;
-      case 11: rc = launch_tma<256, 2048, 2, true>(c, o.s, st, dry); break;
-      case 12: rc = launch_tma<512, 2048, 2, true>(c, o.s, st, dry); break;
-      case 13: rc = launch_tma<128, 512, 3, true>(c, o.s, st, dry); break;
-      case 14: rc = launch_tma<256, 1024, 2, false, 5>(c, o.s, st, dry); break;
-      case 15: rc = launch_tma<256, 1024, 2, false, 6>(c, o.s, st, dry); break;
-      case 16: rc = launch_tma<256, 1024, 2, false, 8>(c, o.s, st, dry); break;
-      case 17: rc = launch_tma<256, 1024, 3, false, 5>(c, o.s, st, dry); break;
-      case 18: rc = launch_tma<128, 512, 2, false, 16>(c, o.s, st, dry); break;
-      case 19: rc = launch_tma<128, 512, 3, false, 12>(c, o.s, st, dry); break;
+      case 9: rc = launch_tma<256, 1024, 2, 1>(c, o.s, st, dry); break;
+      case 10: rc = launch_tma<256, 1024, 3, 1>(c, o.s, st, dry); break;
+      case 11: rc = launch_tma<256, 2048, 2, 1>(c, o.s, st, dry); break;
+      case 12: rc = launch_tma<512, 2048, 2, 1>(c, o.s, st, dry); break;
+      case 13: rc = launch_tma<128, 512, 3, 1>(c, o.s, st, dry); break;
+      case 14: rc = launch_tma<256, 1024, 2, 0, 5>(c, o.s, st, dry); break;
+      case 15: rc = launch_tma<256, 1024, 2, 0, 6>(c, o.s, st, dry); break;
+      case 16: rc = launch_tma<256, 1024, 2, 0, 8>(c, o.s, st, dry); break;
+      case 17: rc = launch_tma<256, 1024, 3, 0, 5>(c, o.s, st, dry); break;
+      case 18: rc = launch_tma<128, 512, 2, 0, 16>(c, o.s, st, dry); break;
+      case 19: rc = launch_tma<128, 512, 3, 0, 12>(c, o.s, st, dry); break;
       case 20: rc = launch_tma2<256, 1024, 3>(c, o.s, st, dry); break;
       case 21: rc = launch_tma2<256, 1024, 4>(c, o.s, st, dry); break;
       case 22: rc = launch_tma2<256, 2048, 3>(c, o.s, st, dry); break;
       case 23: rc = launch_tma2<512, 2048, 3>(c, o.s, st, dry); break;
       case 24: rc = launch_tma2<128, 512, 4>(c, o.s, st, dry); break;
+      case 25: rc = launch_tma<256, 1024, 2, 2>(c, o.s, st, dry); break;
+      case 26: rc = launch_tma<256, 1024, 3, 2>(c, o.s, st, dry); break;
+      case 27: rc = launch_tma<256, 2048, 2, 2>(c, o.s, st, dry); break;
+      case 28: rc = launch_tma<512, 2048, 2, 2>(c, o.s, st, dry); break;
       default: return fail(2, "unknown kernel variant %d", k);
     }
     if (rc) return rc;

@@ -61,6 +61,8 @@ def test_vcycle_parity(built_libs, name, dense_rows):
                                   # 20..24: spmv_tma2_kernel (asynchronous cp.async gathers, fused multiply/reduce)
                                   dict(kernel=20, dense_rows=0), dict(kernel=21, dense_rows=0), dict(kernel=22, dense_rows=0),
                                   dict(kernel=23, dense_rows=0), dict(kernel=24, dense_rows=0),
+                                  # 25..28: nnz-mapped multiply + g-lane (bank-conflict-light) row sums
+                                  dict(kernel=25, dense_rows=0), dict(kernel=26, dense_rows=0), dict(kernel=27, dense_rows=0), dict(kernel=28, dense_rows=0),
                                   dict(kernel=2, ctas_per_sm=1),
                                   # coarse levels collapsed into one dense operator (built from the same kernels at setup)
                                   dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, tail_rows=0, graph=0)],
