@@ -118,6 +118,7 @@ struct DevCSR {
   int nblk = 0;
   int *blk = nullptr;
   int ntiles = 0;
+  int ntiles_int = 0;      // the first ntiles_int tiles reference no ghost column (interior), the rest do (boundary)
   TileDesc *tiles = nullptr;
   DevPlan *xp = nullptr;   // ghost exchange (multi-rank)
   bool is_set = false;
@@ -156,7 +157,7 @@ struct Level {
   bool any_c = false;
 };
 
-enum { OPK_SPMV = 0, OPK_EW = 1, OPK_XCHG = 2, OPK_GATHER0 = 3, OPK_SCATTER0 = 4, OPK_CHILD = 5, OPK_DENSE = 6, OPK_EPOCH = 7, OPK_ACK = 8 };
+enum { OPK_SPMV = 0, OPK_EW = 1, OPK_XCHG = 2, OPK_GATHER0 = 3, OPK_SCATTER0 = 4, OPK_CHILD = 5, OPK_DENSE = 6, OPK_EPOCH = 7, OPK_ACK = 8, OPK_XWAIT = 9 };
 const int kMaxInst = 4096;   // exchange instances per cycle the flag block has room for
 
 struct Op {
@@ -166,6 +167,7 @@ struct Op {
   DevPlan *xp = nullptr;        // OPK_XCHG / OPK_ACK: which plan; xsrc = the vector segment being exchanged
   const double *xsrc = nullptr;
   int inst = -1, ack_inst = -1, ack_delta = 0;   // peer-memory exchange instance (and the one whose acks it waits for)
+  bool async = false;           // OPK_XCHG: run on the side stream, joined by the following OPK_XWAIT
   int level = 0;
   int tag = 0;  // 1 restrict, 2 coarse, 3 A_fc(+W), 4 A_ff residual, 5 inverse, 6 elementwise, 7 fused local smooth, 8 A_cf, 9 A_cc, 10 exchange, 11 dense tail
   double bytes = 0, nnz = 0;
@@ -224,6 +226,9 @@ struct Ctx {
   double *child_b = nullptr, *child_x = nullptr;  // rank 0: global natural vectors of level l_agg
   double ghost_bytes = 0; int xchg_groups = 0;
   // peer-memory ghost exchange (option p2p): one arena per rank = [flag block | ghost buffers], mapped by every peer
+  int overlap = 1;       // NCCL exchange on a side stream, overlapped with the interior tiles of the SpMV
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int p2p = 0;   // 1: peer-memory push/flag exchange (CUDA IPC); 0: NCCL send/recv (measured faster in round 1)
   bool p2p_ready = false;
   char *arena = nullptr; size_t arena_bytes = 0;
@@ -320,6 +325,19 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int s
   std::vector<TileDesc> tiles(tb.size() - 1);
   for (size_t t = 0; t + 1 < tb.size(); ++t) tiles[t] = TileDesc{tb[t], tb[t + 1] - tb[t], h.ia[tb[t]], h.ia[tb[t + 1]] - h.ia[tb[t]]};
   d->ntiles = (int)tiles.size();
+  d->ntiles_int = d->ntiles;
+  if (h.n_ghost > 0) {
+    // interior tiles first: they can be multiplied while the ghost exchange is still in flight
+    std::vector<TileDesc> inner, bnd;
+    for (const TileDesc &t : tiles) {
+      bool ghost = false;
+      for (int k = t.s; k < t.s + t.n && !ghost; ++k) ghost = h.ja[k] >= h.n;
+      (ghost ? bnd : inner).push_back(t);
+    }
+    d->ntiles_int = (int)inner.size();
+    tiles = inner;
+    tiles.insert(tiles.end(), bnd.begin(), bnd.end());
+  }
   if ((rc = dev_upload(c, &d->tiles, tiles))) return rc;
   return 0;
 }
@@ -429,6 +447,17 @@ struct Builder {
     o.kind = OPK_SPMV; o.s = s; o.level = level; o.tag = tag;
     o.bytes = spmv_bytes(A, aux_reads, w) + extra_bytes;
     o.nnz = (double)(A.nnz_model >= 0 ? A.nnz_model : A.nnz);
+    if (xchg && !p2p && use_p2p && c->overlap && c->kernel != 0) {
+      // split-phase MatMult_MPIAIJ: exchange on the side stream || interior tiles; then the boundary tiles
+      out->back().async = true;
+      const double fi = A.ntiles > 0 ? (double)A.ntiles_int / A.ntiles : 1.0;
+      Op oi = o, ob = o;
+      oi.s.ntiles = A.ntiles_int; oi.bytes = o.bytes * fi; oi.nnz = o.nnz * fi;
+      ob.s.tiles = A.tiles + A.ntiles_int; ob.s.ntiles = A.ntiles - A.ntiles_int; ob.bytes = o.bytes - oi.bytes; ob.nnz = o.nnz - oi.nnz;
+      Op wt; wt.kind = OPK_XWAIT; wt.level = level; wt.tag = 10;
+      out->push_back(oi); out->push_back(wt); out->push_back(ob);
+      return;
+    }
     if (p2p) {
       o.s.gw_ready = c->flags() + 64 + (size_t)inst * 32;
       o.s.gw_epoch = c->flags();
@@ -953,6 +982,19 @@ int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op
         Ctx *c = R[0];
         const DevPlan *P = (*progs[0])[i].xp;
         std::string err;
+        if ((*progs[0])[i].async) {   // fork: the pack was launched on the main stream; the NCCL group runs on the side stream
+          CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+          CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+          bool ok2 = c->comm->group_start(&err);
+          for (int p = 0; p < c->nranks && ok2; ++p) {
+            if (P->plan.send_count[p]) ok2 = c->comm->send(P->d_sendbuf + P->plan.send_off[p], (size_t)P->plan.send_count[p], 8, p, c->side, &err);
+            if (ok2 && P->plan.recv_count[p]) ok2 = c->comm->recv(P->d_xg + P->plan.recv_off[p], (size_t)P->plan.recv_count[p], 8, p, c->side, &err);
+          }
+          ok2 = ok2 && c->comm->group_end(&err);
+          if (!ok2) return fail(21, "ghost exchange: %s", err.c_str());
+          CUDA_TRY(cudaEventRecord(c->ev_join, c->side));
+          continue;
+        }
         bool ok = c->comm->group_start(&err);
         for (int p = 0; p < c->nranks && ok; ++p) {
           if (P->plan.send_count[p]) ok = c->comm->send(P->d_sendbuf + P->plan.send_off[p], (size_t)P->plan.send_count[p], 8, p, st, &err);
@@ -963,6 +1005,8 @@ int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op
       } else {
         return fail(21, "ghost exchange requested without a communicator");
       }
+    } else if (kind == OPK_XWAIT) {
+      if (nr == 1 && R[0]->comm) CUDA_TRY(cudaStreamWaitEvent(st, R[0]->ev_join, 0));   // join (in-process groups exchanged synchronously)
     } else if (kind == OPK_GATHER0 || kind == OPK_SCATTER0) {
       const bool gather = kind == OPK_GATHER0;
       if (nr > 1) {
@@ -1878,6 +1922,11 @@ static int create_ctx(Ctx **out, int rank, int nranks, int device, int no_levels
     c->num_sms = prop.multiProcessorCount;
     if (shared_stream) { c->stream = shared_stream; c->own_stream = false; }
     else CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (nranks > 1 && !shared_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
   }
   *out = c.release();
   return 0;
@@ -2197,6 +2246,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   }
   else if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
   else if (k == "pdl") c->pdl = value != 0;
+  else if (k == "overlap") c->overlap = value != 0;
   else if (k == "p2p") {
     if (c->finalized || c->planned) return fail(2, "p2p must be set before finalize_setup");
     c->p2p = value != 0;
@@ -2241,6 +2291,7 @@ static void destroy_ctx(Ctx *c) {
     for (size_t p = 0; p < c->peer_arena.size(); ++p)
       if (c->peer_ipc[p] && c->peer_arena[p]) cudaIpcCloseMemHandle(c->peer_arena[p]);
     for (void *p : c->allocs) cudaFree(p);
+    if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
   }
   c->comm.reset();

@@ -41,10 +41,12 @@ def main():
         xo = hiergen.feed(H, oracle.OracleAIR(H.no_levels)).apply(b)
         parts = hiergen.partition(H, world)
         rg = parts[0].rangesV[0]
-        for agg_rows, p2p in ((0, 1), (600, 1), (600, 0)):      # p2p=1: CUDA-IPC peer-memory exchange, p2p=0: NCCL send/recv
+        # p2p=1: CUDA-IPC peer-memory exchange; p2p=0: NCCL send/recv, with (overlap=1) or without the side-stream split phase
+        for agg_rows, p2p, overlap in ((0, 1, 1), (600, 1, 1), (600, 0, 1), (0, 0, 1), (600, 0, 0)):
             pc = pflare_b200.PC(rank=rank, nranks=world, unique_id=fresh_uid(), device=local).setType("air").setHierarchy(parts[rank])
             pc.setOption("agg_rows", agg_rows)
             pc.setOption("p2p", p2p)
+            pc.setOption("overlap", overlap)
             for rep in range(3):                                 # repeated cycles reuse the ghost buffers (epochs / acks)
                 x = pc.apply(b[rg[rank]:rg[rank + 1]] * (rep + 1))
                 err = np.linalg.norm(x - (rep + 1) * xo[rg[rank]:rg[rank + 1]]) / np.linalg.norm((rep + 1) * xo)

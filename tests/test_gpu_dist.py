@@ -42,7 +42,7 @@ def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
     b = cases.rhs(A.shape[0])
     xo = _oracle(H).apply(b)
     for agg_rows in (0, 600, 10 ** 9):       # fully distributed | coarse levels on rank 0 | everything below level 1 on rank 0
-        x, (l_agg, stats) = _cluster_apply(H, nranks, b, agg_rows=agg_rows, dense_rows=0 if nranks == 3 else 4096)
+        x, (l_agg, stats) = _cluster_apply(H, nranks, b, agg_rows=agg_rows, dense_rows=0 if nranks == 3 else 4096, p2p=1 if nranks == 4 else 0)
         assert cases.rel_l2(x, xo) <= TOL, (name, nranks, agg_rows)
         if agg_rows == 0:
             assert l_agg == H.no_levels + 1
@@ -51,7 +51,7 @@ def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
         assert all(s["exchange_groups"] > 0 for s in stats)
 
 
-@pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=5), dict(dense_rows=0), dict(pdl=0), dict(p2p=0), dict(p2p=0, graph=0)], ids=str)
+@pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=5), dict(dense_rows=0), dict(pdl=0), dict(p2p=1), dict(p2p=1, graph=0), dict(overlap=0), dict(overlap=0, graph=0)], ids=str)
 def test_partitioned_execution_modes(built_libs, opts):
     A, H = cases.build("fd2d_64")
     b = cases.rhs(A.shape[0], seed=3)
@@ -66,6 +66,7 @@ def test_repeated_applies_reuse_ghost_buffers_safely(built_libs):
     parts = hiergen.partition(H, 4)
     cl = pflare_b200.ClusterAIR(H.no_levels, 4)
     cl.set_option("agg_rows", 300)
+    cl.set_option("p2p", 1)
     cl.upload(parts)
     O = _oracle(H)
     for seed in range(5):
