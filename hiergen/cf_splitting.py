@@ -83,7 +83,7 @@ def generate_sabs(a, strong_threshold, symmetrize=True):
     return s
 
 
-def pmisr(S, rng, measure=None, cf=None):
+def pmisr(S, rng, measure=None, cf=None, use_native=True):
     """PMISR Luby loop on a symmetric strength matrix; returns int8 markers (F=-1, C=+1)."""
     n = S.shape[0]
     indptr, cols = S.indptr, S.indices
@@ -92,6 +92,11 @@ def pmisr(S, rng, measure=None, cf=None):
         measure = rng.random(n) + np.diff(indptr)
     if cf is None:
         cf = np.zeros(n, dtype=np.int8)
+    if use_native:
+        from . import native
+        out = native.pmisr(S, measure, cf)
+        if out is not None:
+            return out
     assigned = cf != 0
     zero = (~assigned) & (np.abs(measure) < 1)
     cf[zero] = F_POINT
@@ -115,8 +120,13 @@ def pmisr(S, rng, measure=None, cf=None):
     return cf
 
 
-def diag_dom_ratio(a, cf):
+def diag_dom_ratio(a, cf, use_native=True):
     """Per-F-row sum|a_ij, j in F, j!=i| / |a_ii| (MatDiagDom.F90:98-273)."""
+    if use_native:
+        from . import native
+        out = native.diag_dom_ratio(a, cf)
+        if out is not None:
+            return out[cf == F_POINT]
     rows = _rows_of(a)
     cols = a.indices
     isF = cf == F_POINT

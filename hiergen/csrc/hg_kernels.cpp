@@ -225,4 +225,93 @@ int hg_drop_small(i64 m, const i32* ai, const i32* aj, const double* av, double 
   return bad;
 }
 
+// out = a[rows, :][:, col_map >= 0] with columns relabelled by col_map (MatCreateSubMatrix with sorted index sets).
+// rows == NULL means all rows.  Pass 1 (oj == NULL): per-row counts; pass 2: fill.
+void hg_extract(i64 nrows, const i32* rows, const i32* ai, const i32* aj, const double* av, const i64* col_map, i64* rowcnt,
+                const i64* oi, i32* oj, double* ov) {
+#pragma omp parallel for schedule(static, 4096)
+  for (i64 r = 0; r < nrows; ++r) {
+    const i64 src = rows ? rows[r] : r;
+    i64 cnt = 0, o = oi ? oi[r] : 0;
+    for (i64 p = ai[src]; p < ai[src + 1]; ++p) {
+      const i64 c = col_map[aj[p]];
+      if (c < 0) continue;
+      if (oj) { oj[o] = (i32)c; ov[o] = av[p]; ++o; }
+      ++cnt;
+    }
+    if (rowcnt) rowcnt[r] = cnt;
+  }
+}
+
+// PMISR Luby loop (/root/reference/src/PMISR_Module.F90:271-671), synchronous rounds: an unassigned node joins the set
+// (becomes F, cf = -1) when its measure is below every unassigned neighbour's; its neighbours become assigned (later C).
+// Exact ties: the larger index loses (:519-521).  cf: 0 unassigned on entry (non-zero entries are kept).
+void hg_pmisr(i64 n, const i32* si, const i32* sj, const double* measure, signed char* cf) {
+  std::vector<unsigned char> assigned((size_t)n), inset((size_t)n);
+  i64 remaining = 0;
+  for (i64 i = 0; i < n; ++i) {
+    assigned[(size_t)i] = cf[i] != 0;
+    if (!assigned[(size_t)i] && std::fabs(measure[i]) < 1.0) { cf[i] = -1; assigned[(size_t)i] = 1; }
+    if (!assigned[(size_t)i]) ++remaining;
+  }
+  while (remaining > 0) {
+    i64 nsel = 0;
+#pragma omp parallel for schedule(static, 4096) reduction(+ : nsel)
+    for (i64 i = 0; i < n; ++i) {
+      inset[(size_t)i] = 0;
+      if (assigned[(size_t)i]) continue;
+      bool ok = true;
+      for (i64 p = si[i]; p < si[i + 1] && ok; ++p) {
+        const i32 j = sj[p];
+        if (!assigned[(size_t)j] && !(measure[i] < measure[j])) ok = false;
+      }
+      if (ok) { inset[(size_t)i] = 1; ++nsel; }
+    }
+    if (nsel == 0) {  // ties
+#pragma omp parallel for schedule(static, 4096) reduction(+ : nsel)
+      for (i64 i = 0; i < n; ++i) {
+        inset[(size_t)i] = 0;
+        if (assigned[(size_t)i]) continue;
+        bool ok = true;
+        for (i64 p = si[i]; p < si[i + 1] && ok; ++p) {
+          const i32 j = sj[p];
+          if (assigned[(size_t)j]) continue;
+          if (measure[j] < measure[i]) ok = false;
+          else if (measure[j] == measure[i] && j < i) ok = false;
+        }
+        if (ok) { inset[(size_t)i] = 1; ++nsel; }
+      }
+      if (nsel == 0) break;  // cannot happen on a symmetric strength matrix
+    }
+#pragma omp parallel for schedule(static, 4096)
+    for (i64 i = 0; i < n; ++i) {
+      if (!inset[(size_t)i]) continue;
+      cf[i] = -1;
+      assigned[(size_t)i] = 1;
+      for (i64 p = si[i]; p < si[i + 1]; ++p) assigned[(size_t)sj[p]] = 1;   // benign race: every writer stores 1
+    }
+    remaining = 0;
+#pragma omp parallel for schedule(static, 4096) reduction(+ : remaining)
+    for (i64 i = 0; i < n; ++i) remaining += assigned[(size_t)i] ? 0 : 1;
+  }
+  for (i64 i = 0; i < n; ++i)
+    if (cf[i] == 0) cf[i] = 1;
+}
+
+// per row: sum |a_ij| over F columns j != i, divided by |a_ii| (0 when the diagonal is missing or the row is not F)
+void hg_diag_dom_ratio(i64 n, const i32* ai, const i32* aj, const double* av, const signed char* cf, double* ratio) {
+#pragma omp parallel for schedule(static, 4096)
+  for (i64 i = 0; i < n; ++i) {
+    ratio[i] = 0.0;
+    if (cf[i] != -1) continue;
+    double diag = 0.0, offs = 0.0;
+    for (i64 p = ai[i]; p < ai[i + 1]; ++p) {
+      const i32 j = aj[p];
+      if (cf[j] != -1) continue;
+      if (j == i) diag += std::fabs(av[p]); else offs += std::fabs(av[p]);
+    }
+    if (diag != 0.0) ratio[i] = offs / diag;
+  }
+}
+
 }  // extern "C"

@@ -127,3 +127,55 @@ def _align(acc, S):
     for t, (r, c) in enumerate(zip(rows, S.indices)):
         out[t] = accd.get((r, c), 0.0)
     return out
+
+
+def extract(a, rows, col_map, ncols):
+    """a[rows][:, col_map >= 0] with relabelled columns (native); None if the helper is unavailable."""
+    L = lib()
+    if L is None:
+        return None
+    ai = np.ascontiguousarray(a.indptr, dtype=np.int32)
+    aj = np.ascontiguousarray(a.indices, dtype=np.int32)
+    av = np.ascontiguousarray(a.data, dtype=np.float64)
+    cm = np.ascontiguousarray(col_map, dtype=np.int64)
+    i64, i32, f64 = ctypes.c_int64, ctypes.c_int32, ctypes.c_double
+    if rows is None:
+        nrows, rp = a.shape[0], None
+    else:
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        nrows, rp = rows.size, _p(rows, i32)
+    cnt = np.zeros(nrows, dtype=np.int64)
+    L.hg_extract(i64(nrows), rp, _p(ai, i32), _p(aj, i32), _p(av, f64), _p(cm, i64), _p(cnt, i64), None, None, None)
+    oi = np.zeros(nrows + 1, dtype=np.int64)
+    np.cumsum(cnt, out=oi[1:])
+    oj = np.empty(max(oi[-1], 1), dtype=np.int32)[:oi[-1]]
+    ov = np.empty(max(oi[-1], 1), dtype=np.float64)[:oi[-1]]
+    L.hg_extract(i64(nrows), rp, _p(ai, i32), _p(aj, i32), _p(av, f64), _p(cm, i64), None, _p(oi, i64), _p(oj, i32), _p(ov, f64))
+    return _mk(ov, oj, oi, (nrows, ncols))
+
+
+def pmisr(S, measure, cf):
+    L = lib()
+    if L is None:
+        return None
+    si = np.ascontiguousarray(S.indptr, dtype=np.int32)
+    sj = np.ascontiguousarray(S.indices, dtype=np.int32)
+    me = np.ascontiguousarray(measure, dtype=np.float64)
+    cf = np.ascontiguousarray(cf, dtype=np.int8)
+    L.hg_pmisr(ctypes.c_int64(S.shape[0]), _p(si, ctypes.c_int32), _p(sj, ctypes.c_int32), _p(me, ctypes.c_double),
+               cf.ctypes.data_as(ctypes.POINTER(ctypes.c_byte)))
+    return cf
+
+
+def diag_dom_ratio(a, cf):
+    L = lib()
+    if L is None:
+        return None
+    ai = np.ascontiguousarray(a.indptr, dtype=np.int32)
+    aj = np.ascontiguousarray(a.indices, dtype=np.int32)
+    av = np.ascontiguousarray(a.data, dtype=np.float64)
+    cf8 = np.ascontiguousarray(cf, dtype=np.int8)
+    out = np.zeros(a.shape[0])
+    L.hg_diag_dom_ratio(ctypes.c_int64(a.shape[0]), _p(ai, ctypes.c_int32), _p(aj, ctypes.c_int32), _p(av, ctypes.c_double),
+                        cf8.ctypes.data_as(ctypes.POINTER(ctypes.c_byte)), _p(out, ctypes.c_double))
+    return out

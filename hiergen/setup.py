@@ -132,6 +132,14 @@ def _submatrix(a, row_idx, col_map, ncols):
     return out
 
 
+def _extract(a, rows, col_map, ncols):
+    """a[rows][:, kept cols] through the native helper (falls back to scipy)."""
+    out = native.extract(a, rows, col_map, ncols)
+    if out is None:
+        out = _submatrix(a[rows].tocsr(), None, col_map, ncols)
+    return out
+
+
 def _clamp_orders(n_rows, poly_order, sparsity_order):
     """setup_gmres_poly_data (Gmres_Poly.F90:40-86)."""
     po = poly_order
@@ -256,11 +264,9 @@ def build_hierarchy(A, opts: AirOptions = None, verbose=False):
             break
         fmap = np.full(n, -1, dtype=np.int64); fmap[is_f] = np.arange(nf)
         cmap = np.full(n, -1, dtype=np.int64); cmap[is_c] = np.arange(nc)
-        Af = cur[is_f].tocsr()
-        A_ff = _submatrix(Af, None, fmap, nf)
-        A_fc = _submatrix(Af, None, cmap, nc)
-        Ac = cur[is_c].tocsr()
-        A_cf = _submatrix(Ac, None, fmap, nf)
+        A_ff = _extract(cur, is_f, fmap, nf)
+        A_fc = _extract(cur, is_f, cmap, nc)
+        A_cf = _extract(cur, is_c, fmap, nf)
         smooth = list(opts.smooth_order)
         inv_type = opts.inverse_type
         sparsity = opts.inverse_sparsity_order
@@ -307,7 +313,7 @@ def build_hierarchy(A, opts: AirOptions = None, verbose=False):
                    R=R, P=P, smooth_order=smooth, aff_diag=aff_diag)
         if opts.any_c_smooths:
             lv.A_cf = _i32(A_cf)
-            lv.A_cc = _i32(_submatrix(Ac, None, cmap, nc))
+            lv.A_cc = _i32(_extract(cur, is_c, cmap, nc))
             lv.inv_A_cc, _ = make_inverse(lv.A_cc, opts.c_inverse_type, opts.c_poly_order,
                                           opts.c_inverse_sparsity_order, opts.matrix_free_polys,
                                           opts.diag_scale_polys, rng)

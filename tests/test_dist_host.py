@@ -77,6 +77,7 @@ def test_ghost_plans_in_process_group(built_libs, name, nranks, agg_rows):
 
     # the plans drive correct distributed products (exchange emulated in-process: rank r receives
     # exactly what rank p packed for it)
+    _PACKS.clear()   # keyed by id(cl): must not survive from a previous (garbage-collected) group
     worst = max(_products_with_lookup(H, parts, r, nranks, cl, l_agg) for r in range(nranks))
     assert worst < 1e-13
     # no GPU bound: apply must refuse
