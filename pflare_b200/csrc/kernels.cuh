@@ -53,7 +53,6 @@ struct SpmvOp {
   // fully local F smooth (diagonal A_ff and diagonal inverse): x = wout value; repeat fd_its:
   // x += fd_m[i] * (v - fd_a[i] * x); wout[i] = x
   const double *fd_a, *fd_m; int fd_its;
-  int dbg_seq;                 // measurement only: gather x sequentially instead of through col (wrong results)
   // peer-memory ghost exchange: before the first ghost read, wait until every source rank has pushed
   // its chunk of THIS exchange instance (ready[q] >= *epoch for the ranks q in srcmask)
   const unsigned *gw_ready; const unsigned *gw_epoch; unsigned gw_srcmask;
@@ -325,7 +324,7 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
     const TileDesc d = sdesc[slot];
     // when to issue the bulk copies of tile it+STAGES-1 (its slot was freed by the barrier ending
     // iteration it-1): normally right after this tile's gathers have been queued
-    const bool late_issue = !ROWMAP && op.dbg_seq != 6 && op.dbg_seq != 2 && d.n <= TILE;
+    const bool late_issue = !ROWMAP && d.n <= TILE;
     if (!late_issue && tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
     Stage &S = stages[slot];
     if (d.n <= TILE) {
@@ -336,15 +335,9 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
       }
       const bool has_row = (ROWMAP || GRED) ? (tid < d.nrows * g && (tid & (g - 1)) == 0) : (tid < d.nrows);
       EpiPre pre;
-      if (has_row && op.dbg_seq != 2 && op.dbg_seq != 5) pre = epi_prefetch(op, d.r0 + ((ROWMAP || GRED) ? tid / g : tid));
+      if (has_row) pre = epi_prefetch(op, d.r0 + ((ROWMAP || GRED) ? tid / g : tid));
       mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
       const int o = d.s & 3;
-      if (op.dbg_seq == 2) {  // measurement only: TMA stream + barriers, no work
-        if (tid == 0 && S.val[o] == 1.2345e300) op.out[0] = 0.0;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        continue;
-      }
       if (ROWMAP) {
         // g lanes per row (g = largest power of two with nrows * g <= NT, at most 32): lanes of
         // neighbouring rows gather neighbouring x entries, so a warp's gather touches few lines
@@ -373,10 +366,7 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
           const int k = tid + k0 * NT;
           xr[k0] = 0.0;
           if (k < d.n) {
-            int c = S.col[o + k];
-            if (op.dbg_seq == 1) c = (d.r0 + k) % op.nloc;
-            if (op.dbg_seq >= 3 && op.dbg_seq <= 5) xr[k0] = (double)c;   // measurement only: no gather
-            else xr[k0] = gather_x(op, c);
+            xr[k0] = gather_x(op, S.col[o + k]);
           }
         }
         // the latency-critical gathers of THIS tile are queued ahead of the next tile's bulk copies
@@ -412,8 +402,7 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
           if (op.wlast) { --q; xw = S.val[q]; }
           double sum = 0.0;
           for (; p < q; ++p) sum += S.val[p];
-          if (op.dbg_seq == 5) { if (sum == 1.2345e300) op.out[0] = 0.0; }   // measurement only: no epilogue
-          else epi_finish(op, d.r0 + tid, sum, xw, pre);
+          epi_finish(op, d.r0 + tid, sum, xw, pre);
         }
       }
     } else {

@@ -210,7 +210,6 @@ struct Ctx {
   int kernel = 1;        // 0: smem-staged stream kernel, 1..: TMA-pipelined variants (kVariants)
   int tile_kernel = 1;   // the variant the uploaded tile lists were built for
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
-  int dbg_seq = 0;       // measurement only (wrong results): sequential instead of indexed x gathers
   int pdl = 1;           // programmatic dependent launch between the kernels of the cycle
   int64_t agg_rows = 262144;  // levels with <= this many GLOBAL rows are agglomerated onto rank 0 (multi-rank)
   int num_sms = 148;
@@ -421,7 +420,7 @@ struct Builder {
   SpmvOp base(const DevCSR &A, const double *x) {
     SpmvOp s{};
     s.rp = A.rp; s.col = A.col; s.val = A.val; s.m = A.m; s.nblk = A.nblk; s.blk = A.blk;
-    s.tiles = A.tiles; s.ntiles = A.ntiles; s.dbg_seq = c->dbg_seq;
+    s.tiles = A.tiles; s.ntiles = A.ntiles;
     s.x = x; s.nloc = A.n; s.beta = 1.0;
     s.xg = A.xp ? A.xp->d_xg : nullptr;
     return s;
@@ -2251,12 +2250,11 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
     if (c->finalized || c->planned) return fail(2, "p2p must be set before finalize_setup");
     c->p2p = value != 0;
   }
-  else if (k == "dbg_seq_gather") c->dbg_seq = (int)value;
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
     Ctx *ch = c->child.get();
     ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->kernel = c->kernel; ch->ctas_per_sm = c->ctas_per_sm;
-    ch->dbg_seq = c->dbg_seq; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
+    ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   }
   return 0;
 }
