@@ -17,6 +17,13 @@ from dist_emul import distributed_products
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _reassemble(parts, l, which, shape):
     blocks = []
     for lh in parts:
@@ -145,7 +152,7 @@ def test_work_model_matches_reference_nnz_count(built_libs):
 
 def test_gloo_two_processes(built_libs):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_gloo_check.py")]
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_gloo_check.py")]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]

@@ -18,6 +18,13 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _oracle(H):
     return hiergen.feed(H, oracle.OracleAIR(H.no_levels))
 
@@ -118,7 +125,7 @@ def test_nccl_two_processes(built_libs):
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29541", os.path.join(root, "tests", "dist_nccl_check.py")]
+           "--master-port", str(_free_port()), os.path.join(root, "tests", "dist_nccl_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "NCCL_DIST_OK" in out.stdout
