@@ -56,6 +56,10 @@ struct SpmvOp {
   // peer-memory ghost exchange: before the first ghost read, wait until every source rank has pushed
   // its chunk of THIS exchange instance (ready[q] >= *epoch for the ranks q in srcmask)
   const unsigned *gw_ready; const unsigned *gw_epoch; unsigned gw_srcmask;
+  // wide-tile kernel: up to 3 epilogue operand arrays travel with the tile as TMA bulk copies
+  // (field ids: 1 aux, 2 D, 3 x_i (Neumann), 4 fd_a, 5 fd_m, 6 out (read-modify-write), 7 acc_src, 8 acc)
+  unsigned char stg_field[3]; unsigned char n_stg; unsigned stg_mask;
+  int wide;                    // this operator's tile list was built for spmv_tma_wide_kernel
 };
 
 // out[i] (=|+=) alpha * a[i] * (b ? b[i] : 1) / (dv ? dv[i] : 1)
@@ -123,6 +127,44 @@ __device__ __forceinline__ EpiPre epi_prefetch(const SpmvOp &op, int i) {
   p.accsrc = (op.acc_mode && op.acc_src) ? op.acc_src[i] : 0.0;
   p.acc = op.acc_mode == 2 ? op.acc[i] : 0.0;
   return p;
+}
+
+__device__ __forceinline__ const double *epi_field_ptr(const SpmvOp &op, int f) {
+  switch (f) {
+    case 1: return op.aux;
+    case 2: return op.D;
+    case 3: return op.x;
+    case 4: return op.fd_a;
+    case 5: return op.fd_m;
+    case 6: return op.out;
+    case 7: return op.acc_src;
+    default: return op.acc;
+  }
+}
+// epi_prefetch for the fields that were NOT staged (mask bit f-1 set = staged)
+__device__ __forceinline__ EpiPre epi_prefetch_masked(const SpmvOp &op, int i, unsigned m) {
+  EpiPre p;
+  p.aux = (op.aux && !(m & 1u)) ? op.aux[i] : 0.0;
+  p.D = (op.D && !(m & 2u)) ? op.D[i] : 1.0;
+  p.xi = (op.neumann && !(m & 4u)) ? op.x[i] : 0.0;
+  p.fa = (op.fd_its > 0 && !(m & 8u)) ? op.fd_a[i] : 0.0;
+  p.fm = (op.fd_its > 0 && !(m & 16u)) ? op.fd_m[i] : 0.0;
+  p.out = (op.out_mode == 2 && !(m & 32u)) ? op.out[i] : 0.0;
+  p.accsrc = (op.acc_mode && op.acc_src && !(m & 64u)) ? op.acc_src[i] : 0.0;
+  p.acc = (op.acc_mode == 2 && !(m & 128u)) ? op.acc[i] : 0.0;
+  return p;
+}
+__device__ __forceinline__ void epi_set_field(EpiPre &p, int f, double v) {
+  switch (f) {
+    case 1: p.aux = v; break;
+    case 2: p.D = v; break;
+    case 3: p.xi = v; break;
+    case 4: p.fa = v; break;
+    case 5: p.fm = v; break;
+    case 6: p.out = v; break;
+    case 7: p.accsrc = v; break;
+    default: p.acc = v; break;
+  }
 }
 
 __device__ __forceinline__ void epi_finish(const SpmvOp &op, int i, double s, double xw, const EpiPre &p) {
@@ -551,6 +593,139 @@ __global__ void __launch_bounds__(NT) spmv_tma2_kernel(const SpmvOp op) {
       }
       if (active && lg == 0) epi_finish(op, d.r0 + row, sum, xw, pre);
     } else {
+      const int e = d.s + d.n;
+      const int last = op.wlast ? e - 1 : e;
+      double part = 0.0;
+      for (int k = d.s + tid; k < last; k += NT) part += ld_stream(op.val + k) * gather_x(op, ld_stream(op.col + k));
+#pragma unroll
+      for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(0xffffffffu, part, w);
+      if ((tid & 31) == 0) red[tid >> 5] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < NT / 32; ++w) sum += red[w];
+        const double xw = op.wlast ? op.val[last] * gather_x(op, op.col[last]) : 0.0;
+        row_epilogue(op, d.r0, sum, xw);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Wide-tile TMA kernel for operators with very short rows (levels 1-4 of upwind problems: 1-3 nonzeros
+// per row).  With <= NT rows per tile such a tile moves only ~5 KB while the per-tile latency chain
+// (wait, gather, barrier, reduce, barrier) is ~1.5 us regardless of its size; here a tile holds up to
+// MAXROWS = 4 NT rows, every thread reduces up to 4 rows, and the rows' epilogue operands arrive with the
+// tile as extra bulk copies (contiguous row range) instead of per-thread register prefetches.
+template <int TILE, int MAXROWS, int NOPD>
+struct WideStage {
+  double val[TILE + 8];
+  double opd[NOPD][MAXROWS + 2];
+  int col[TILE + 8];
+  int rp[MAXROWS + 8];
+};
+
+template <int NT, int TILE, int MAXROWS, int STAGES>
+__global__ void __launch_bounds__(NT) spmv_tma_wide_kernel(const SpmvOp op) {
+  constexpr int NOPD = 3;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  typedef WideStage<TILE, MAXROWS, NOPD> Stage;
+  Stage *stages = reinterpret_cast<Stage *>(smem_raw);
+  __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ TileDesc sdesc[STAGES];
+  __shared__ int sshift[STAGES][NOPD];
+  __shared__ double red[NT / 32 + 1];
+  const int tid = threadIdx.x;
+  const TileDesc *__restrict__ tiles = op.tiles;
+  const int ntiles = op.ntiles;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_tiles = (first < ntiles) ? (ntiles - first + stride - 1) / stride : 0;
+  const int nstg = op.n_stg;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint64_t pol = l2_policy_evict_first();
+  TileDesc dnext = {0, 0, 0, 0};
+  if (tid == 0 && my_tiles > 0) dnext = tiles[first];
+  auto issue = [&](int j) {
+    const TileDesc d = dnext;
+    if (j + 1 < my_tiles) dnext = tiles[first + (j + 1) * stride];
+    const int slot = j % STAGES;
+    sdesc[slot] = d;
+    if (d.n <= TILE) {
+      Stage &S = stages[slot];
+      const int s_al = d.s & ~3;
+      const int cnt = (d.n + (d.s - s_al) + 3) & ~3;
+      const int r_al = d.r0 & ~3;
+      const int rcnt = (d.nrows + 1 + (d.r0 - r_al) + 3) & ~3;
+      uint32_t bytes = (uint32_t)(cnt * 12 + rcnt * 4);
+      unsigned long long a_al[NOPD]; uint32_t ob[NOPD];
+      for (int k = 0; k < nstg; ++k) {
+        const unsigned long long a = (unsigned long long)(epi_field_ptr(op, op.stg_field[k]) + d.r0);
+        a_al[k] = a & ~15ull;
+        const int sh = (int)((a - a_al[k]) >> 3);
+        sshift[slot][k] = sh;
+        ob[k] = (uint32_t)(((d.nrows + sh + 1) & ~1) * 8);
+        bytes += ob[k];
+      }
+      mbar_expect_tx(&full[slot], bytes);
+      tma_load_1d(S.val, op.val + s_al, (uint32_t)(cnt * 8), &full[slot], pol);
+      tma_load_1d(S.col, op.col + s_al, (uint32_t)(cnt * 4), &full[slot], pol);
+      tma_load_1d(S.rp, op.rp + r_al, (uint32_t)(rcnt * 4), &full[slot], pol);
+      for (int k = 0; k < nstg; ++k) tma_load_1d(S.opd[k], (const void *)a_al[k], ob[k], &full[slot], pol);
+    } else {
+      mbar_expect_tx(&full[slot], 0);
+    }
+  };
+  pdl_launch_dependents();
+  pdl_wait();   // the staged operands are vectors written by the previous kernels
+  if (tid == 0) {
+    ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+    for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);
+  }
+  __syncthreads();
+
+  for (int it = 0; it < my_tiles; ++it) {
+    const int slot = it % STAGES;
+    const TileDesc d = sdesc[slot];
+    Stage &S = stages[slot];
+    mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
+    if (d.n <= TILE) {
+      const int o = d.s & 3;
+      constexpr int kIter = TILE / NT;
+      double xr[kIter];
+#pragma unroll
+      for (int k0 = 0; k0 < kIter; ++k0) {
+        const int k = tid + k0 * NT;
+        xr[k0] = 0.0;
+        if (k < d.n) xr[k0] = gather_x(op, S.col[o + k]);
+      }
+      if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
+#pragma unroll
+      for (int k0 = 0; k0 < kIter; ++k0) {
+        const int k = tid + k0 * NT;
+        if (k < d.n) S.val[o + k] = S.val[o + k] * xr[k0];
+      }
+      __syncthreads();
+      const int ro = d.r0 & 3;
+      for (int r = tid; r < d.nrows; r += NT) {
+        int p = S.rp[ro + r] - d.s + o;
+        int q = S.rp[ro + r + 1] - d.s + o;
+        double xw = 0.0;
+        if (op.wlast) { --q; xw = S.val[q]; }
+        double sum = 0.0;
+        for (; p < q; ++p) sum += S.val[p];
+        EpiPre pre = epi_prefetch_masked(op, d.r0 + r, op.stg_mask);
+        for (int k = 0; k < nstg; ++k) epi_set_field(pre, op.stg_field[k], S.opd[k][sshift[slot][k] + r]);
+        epi_finish(op, d.r0 + r, sum, xw, pre);
+      }
+    } else {
+      if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
       const int e = d.s + d.n;
       const int last = op.wlast ? e - 1 : e;
       double part = 0.0;

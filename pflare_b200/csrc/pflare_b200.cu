@@ -121,6 +121,7 @@ struct DevCSR {
   int ntiles_int = 0;      // the first ntiles_int tiles reference no ghost column (interior), the rest do (boundary)
   TileDesc *tiles = nullptr;
   DevPlan *xp = nullptr;   // ghost exchange (multi-rank)
+  bool wide = false;       // very short rows: tiles of up to 1024 rows for spmv_tma_wide_kernel
   bool is_set = false;
   bool valid() const { return is_set; }
 };
@@ -225,6 +226,8 @@ struct Ctx {
   double *child_b = nullptr, *child_x = nullptr;  // rank 0: global natural vectors of level l_agg
   double ghost_bytes = 0; int xchg_groups = 0;
   // peer-memory ghost exchange (option p2p): one arena per rank = [flag block | ghost buffers], mapped by every peer
+  int wide_min_rows = 32768;
+  double wide_rows = 4.0; // operators with fewer nonzeros per row than this (and >= 32768 rows) use the wide-tile kernel (0 = off)
   int overlap = 1;       // NCCL exchange on a side stream, overlapped with the interior tiles of the SpMV
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -242,7 +245,7 @@ struct Ctx {
 template <class T>
 int dev_alloc(Ctx *c, T **p, size_t n) {
   void *q = nullptr;
-  size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  size_t bytes = std::max<size_t>(n, 1) * sizeof(T) + 64;   // slack: bulk copies round their extent up to 16 bytes
   CUDA_TRY(cudaMalloc(&q, bytes));
   c->allocs.push_back(q);
   c->dev_bytes += (double)bytes;
@@ -320,7 +323,8 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int s
   d->nblk = (int)blk.size() - 1;
   if ((rc = dev_upload(c, &d->blk, blk))) return rc;
   const Variant &V = kVariants[c->tile_kernel];
-  std::vector<int> tb = make_blocks(h.ia, h.m, V.tile, V.nt);
+  d->wide = c->kernel != 0 && c->wide_rows > 0 && h.m >= c->wide_min_rows && (double)h.nnz() < c->wide_rows * (double)h.m;
+  std::vector<int> tb = d->wide ? make_blocks(h.ia, h.m, 1024, 1024) : make_blocks(h.ia, h.m, V.tile, V.nt);
   std::vector<TileDesc> tiles(tb.size() - 1);
   for (size_t t = 0; t + 1 < tb.size(); ++t) tiles[t] = TileDesc{tb[t], tb[t + 1] - tb[t], h.ia[tb[t]], h.ia[tb[t + 1]] - h.ia[tb[t]]};
   d->ntiles = (int)tiles.size();
@@ -423,6 +427,7 @@ struct Builder {
     s.tiles = A.tiles; s.ntiles = A.ntiles;
     s.x = x; s.nloc = A.n; s.beta = 1.0;
     s.xg = A.xp ? A.xp->d_xg : nullptr;
+    s.wide = A.wide ? 1 : 0;
     return s;
   }
   void push_spmv(const SpmvOp &s, const DevCSR &A, int tag, int aux_reads, int w, double extra_bytes = 0) {
@@ -446,6 +451,15 @@ struct Builder {
     o.kind = OPK_SPMV; o.s = s; o.level = level; o.tag = tag;
     o.bytes = spmv_bytes(A, aux_reads, w) + extra_bytes;
     o.nnz = (double)(A.nnz_model >= 0 ? A.nnz_model : A.nnz);
+    if (A.wide) {
+      // which epilogue operands travel with the tile (at most 3, in this priority); the rest are loaded per row
+      const bool need[9] = {false, s.aux != nullptr, s.D != nullptr, s.neumann != 0, s.fd_its > 0, s.fd_its > 0, s.out_mode == 2,
+                            s.acc_mode != 0 && s.acc_src != nullptr, s.acc_mode == 2};
+      const int order[8] = {1, 6, 4, 5, 2, 3, 7, 8};
+      o.s.n_stg = 0; o.s.stg_mask = 0;
+      for (int f : order)
+        if (need[f] && o.s.n_stg < 3) { o.s.stg_field[o.s.n_stg++] = (unsigned char)f; o.s.stg_mask |= 1u << (f - 1); }
+    }
     if (xchg && !p2p && use_p2p && c->overlap && c->kernel != 0) {
       // split-phase MatMult_MPIAIJ: exchange on the side stream || interior tiles; then the boundary tiles
       out->back().async = true;
@@ -823,6 +837,23 @@ int launch_tma2(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   return 0;
 }
 
+template <int NT, int TILE, int MAXROWS, int STAGES>
+int launch_wide(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  auto kern = spmv_tma_wide_kernel<NT, TILE, MAXROWS, STAGES>;
+  const size_t smem = sizeof(WideStage<TILE, MAXROWS, 3>) * STAGES;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem));
+    per_sm = std::max(nb, 1);
+  }
+  if (dry) return 0;
+  const int grid = std::min(s.ntiles, c->num_sms * per_sm);
+  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, NT, smem, st, s));
+  return 0;
+}
+
 __global__ void __launch_bounds__(kThreads) pack_kernel(int n, const int *__restrict__ idx, const double *__restrict__ x, double *__restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];
 }
@@ -841,6 +872,11 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
     if (!dry && (o.s.m == 0 || o.s.ntiles == 0)) return 0;
     int rc = 0;
     const int k = c->kernel;
+    if (k != 0 && (o.s.wide || dry)) {
+      rc = launch_wide<256, 1024, 1024, 2>(c, o.s, st, dry);
+      if (rc) return rc;
+      if (!dry) { CUDA_TRY(cudaGetLastError()); return 0; }
+    }
     switch (k) {
       case 0: {
         if (dry) return 0;
@@ -1296,7 +1332,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
   ch->use_graph = 0; ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
-  ch->kernel = c->kernel; ch->tile_kernel = c->tile_kernel; ch->ctas_per_sm = c->ctas_per_sm;
+  ch->kernel = c->kernel; ch->tile_kernel = c->tile_kernel; ch->ctas_per_sm = c->ctas_per_sm; ch->wide_rows = c->wide_rows; ch->wide_min_rows = c->wide_min_rows;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
   for (int l = LA; l <= NL; ++l) {
@@ -2246,6 +2282,14 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
   else if (k == "pdl") c->pdl = value != 0;
   else if (k == "overlap") c->overlap = value != 0;
+  else if (k == "wide_min_rows") {
+    if (c->finalized || c->planned) return fail(2, "wide_min_rows must be set before finalize_setup");
+    c->wide_min_rows = (int)value;
+  }
+  else if (k == "wide_rows") {
+    if (c->finalized || c->planned) return fail(2, "wide_rows must be set before finalize_setup");
+    c->wide_rows = value;
+  }
   else if (k == "p2p") {
     if (c->finalized || c->planned) return fail(2, "p2p must be set before finalize_setup");
     c->p2p = value != 0;

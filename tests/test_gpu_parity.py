@@ -64,10 +64,14 @@ def test_vcycle_parity(built_libs, name, dense_rows):
                                   # 25..28: nnz-mapped multiply + g-lane (bank-conflict-light) row sums
                                   dict(kernel=25, dense_rows=0), dict(kernel=26, dense_rows=0), dict(kernel=27, dense_rows=0), dict(kernel=28, dense_rows=0),
                                   dict(kernel=2, ctas_per_sm=1),
+                                  # wide-tile kernel (up to 1024 rows per tile, TMA-staged epilogue operands) forced onto every operator
+                                  dict(wide_min_rows=0, wide_rows=1e9, dense_rows=0), dict(wide_min_rows=0, dense_rows=0),
+                                  dict(wide_min_rows=0, wide_rows=1e9, dense_rows=0, graph=0, pdl=0), dict(wide_rows=0, dense_rows=0),
                                   # coarse levels collapsed into one dense operator (built from the same kernels at setup)
                                   dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, tail_rows=0, graph=0)],
                          ids=lambda o: ",".join("%s=%g" % kv for kv in o.items()))
-@pytest.mark.parametrize("name", ["fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "fd2d_diagAff", "dg_mf", "fd2d_idealW"])
+@pytest.mark.parametrize("name", ["fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "fd2d_diagAff", "dg_mf", "fd2d_idealW",
+                                  "fd2d_mf_neumann", "fd2d_mf_newton_noextra_dscale"])
 def test_vcycle_parity_execution_modes(built_libs, name, opts):
     A, H = cases.build(name)
     b = cases.rhs(A.shape[0], seed=7)
