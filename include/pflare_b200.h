@@ -180,7 +180,12 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
  * per PETSc call), "kernel" (SpMV kernel variant; 0 = first-generation smem-staged kernel, 1.. =
  * TMA-pipelined variants; variants other than 0 must be chosen before finalize_setup), "ctas_per_sm",
  * "agg_rows" (multi-rank, before finalize_setup: levels with <= this many global rows are agglomerated
- * onto rank 0; 0 = never). */
+ * onto rank 0; 0 = never), "dense_rows" (levels with <= this many rows are collapsed into one dense
+ * operator built from the same kernels at setup; 0 = off), "pdl" (programmatic dependent launch),
+ * "overlap" (NCCL exchange on a side stream under the interior tiles), "p2p" (before finalize_setup:
+ * peer-memory push exchange over CUDA IPC instead of NCCL), "wide_rows" / "wide_min_rows" (before
+ * finalize_setup: operators with fewer nonzeros per row / at least that many rows use the wide-tile
+ * kernel; off by default). */
 int pflare_b200_set_option(void *handle, const char *key, double value);
 
 const char *pflare_b200_last_error(void);

@@ -227,7 +227,8 @@ struct Ctx {
   double ghost_bytes = 0; int xchg_groups = 0;
   // peer-memory ghost exchange (option p2p): one arena per rank = [flag block | ghost buffers], mapped by every peer
   int wide_min_rows = 32768;
-  double wide_rows = 4.0; // operators with fewer nonzeros per row than this (and >= 32768 rows) use the wide-tile kernel (0 = off)
+  double wide_rows = 0.0; // operators with fewer nonzeros per row than this (and >= wide_min_rows rows) use the wide-tile kernel
+                          // (0 = off, the default: measured 15 % slower per cycle than 256-row tiles in round 1)
   int overlap = 1;       // NCCL exchange on a side stream, overlapped with the interior tiles of the SpMV
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
