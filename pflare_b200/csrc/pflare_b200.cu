@@ -1900,7 +1900,8 @@ int apply_ctx(Ctx *c, const double *b, double *x, int on_device) {
 }
 
 // ops of one inverse apply (PCPFLAREINV / seam 3) on a context; in/out are c->bb / c->xb
-int build_inv_ops(Ctx *c, int our_level, int which, std::vector<Op> *ops, int *n_out, const int **perm, const int **iperm) {
+int build_inv_ops(Ctx *c, int our_level, int which, std::vector<Op> *ops, int *n_out, const int **perm, const int **iperm,
+                  const double *src = nullptr, double *dst = nullptr) {
   if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);
   if (c->l_agg <= c->no_levels && our_level >= c->l_agg) return fail(2, "level %d is agglomerated on rank 0; its inverse cannot be applied on its own", our_level);
   Level &Lv = c->L[our_level];
@@ -1922,7 +1923,9 @@ int build_inv_ops(Ctx *c, int our_level, int which, std::vector<Op> *ops, int *n
   if (I->kind == 0) return fail(4, "that inverse was not set");
   Builder B{c, ops};
   B.level = our_level;
-  if ((rc = B.emit_inv(*I, *A, Ad, n, c->bb, c->xb, 1))) return rc;
+  // INV_AFF needs no permutation: the caller's vectors can be used in place (src / dst given)
+  const bool direct = src && dst && *perm == nullptr;
+  if ((rc = B.emit_inv(*I, *A, Ad, n, direct ? src : c->bb, direct ? dst : c->xb, 1))) return rc;
   *n_out = n;
   return 0;
 }
@@ -2068,19 +2071,23 @@ int pflare_b200_inv_apply(void *handle, int our_level, int which, const double *
   if (c->device < 0) return fail(10, "host-only planning context: no CUDA device bound");
   if (!c->finalized) return fail(6, "inv_apply called before finalize_setup");
   if (c->cluster) return fail(2, "this handle belongs to an in-process rank group: call pflare_b200_cluster_inv_apply");
-  std::vector<Op> ops;
-  int n = 0; const int *perm, *iperm;
-  if ((rc = build_inv_ops(c, our_level, which, &ops, &n, &perm, &iperm))) return rc;
+  const int n_guess = (our_level >= 1 && our_level <= c->no_levels)
+                          ? (which == PFLARE_B200_INV_ACC ? c->L[our_level].nc : (our_level == c->no_levels ? c->L[our_level].n : c->L[our_level].nf)) : 0;
   const double *xd = x; double *yd = y;
   if (!on_device) {
-    CUDA_TRY(cudaMemcpyAsync(c->io_b, x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);
+    CUDA_TRY(cudaMemcpyAsync(c->io_b, x, (size_t)n_guess * 8, cudaMemcpyHostToDevice, c->stream));
     xd = c->io_b; yd = c->io_x;
   }
-  if ((rc = launch_ew_now(c, n, xd, c->bb, iperm, nullptr, c->stream))) return rc;
+  std::vector<Op> ops;
+  int n = 0; const int *perm, *iperm;
+  const bool direct = which == PFLARE_B200_INV_AFF;   // no permutation: run on the caller's (or the staging) vectors in place
+  if ((rc = build_inv_ops(c, our_level, which, &ops, &n, &perm, &iperm, direct ? xd : nullptr, direct ? yd : nullptr))) return rc;
+  if (!direct && (rc = launch_ew_now(c, n, xd, c->bb, iperm, nullptr, c->stream))) return rc;
   std::vector<Ctx *> R{c};
   std::vector<const std::vector<Op> *> Pp{&ops};
   if ((rc = exec_ops(R, Pp, 0, (int)ops.size(), c->stream))) return rc;
-  if ((rc = launch_ew_now(c, n, c->xb, yd, perm, nullptr, c->stream))) return rc;
+  if (!direct && (rc = launch_ew_now(c, n, c->xb, yd, perm, nullptr, c->stream))) return rc;
   if (!on_device) {
     CUDA_TRY(cudaMemcpyAsync(y, c->io_x, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
