@@ -87,6 +87,125 @@ __global__ void __launch_bounds__(NT) spmv_v0(const double *__restrict__ val, co
   }
 }
 
+// ------------------------------------------------------------------------------------------ V0F
+// V0 plus, bit by bit, the generality of the product kernel (FEAT bitmask):
+//   1 rows through a row-pointer tile (third bulk copy) and a run-time row loop
+//   2 tile descriptors read from global memory (one-ahead prefetch), run-time tile extents and guards
+//   4 L2 evict-first policy on the bulk copies
+//   8 generic run-time-branched epilogue (the product's SpmvOp epilogue)
+struct TileD { int r0, nrows, s, n; };
+struct GenEpi {
+  const double *D; int neumann; const double *aux; double alpha, beta; double *out; int out_mode; double *out2; double delta;
+  double *acc; double gamma; const double *acc_src; int acc_mode; int wlast; double *wout; const double *fd_a, *fd_m; int fd_its;
+  const double *x;
+};
+__device__ __forceinline__ void tma1d_pol(void *dst, const void *src, uint32_t n, uint64_t *b, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)), "l"(src), "r"(n), "r"(smem_u32(b)), "l"(pol) : "memory");
+}
+template <int NT, int TILE, int STAGES, int L, int FEAT>
+__global__ void __launch_bounds__(NT) spmv_v0f(const double *__restrict__ val, const int *__restrict__ col, const int *__restrict__ rp,
+                                              const TileD *__restrict__ tiles, const double *__restrict__ x, const double *__restrict__ b,
+                                              double *__restrict__ y, int ntiles, const GenEpi ge) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int ROWS = TILE / L;
+  struct Stage { double v[TILE + 8]; int c[TILE + 8]; int r[ROWS + 8]; };
+  Stage *st = reinterpret_cast<Stage *>(smem);
+  __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ TileD sdesc[STAGES];
+  const int tid = threadIdx.x;
+  if (tid == 0) { for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  uint64_t pol = 0;
+  if (FEAT & 4) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int mine = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+  TileD dnext = {0, 0, 0, 0};
+  if ((FEAT & 2) && tid == 0 && mine > 0) dnext = tiles[first];
+  auto issue = [&](int j) {
+    const int slot = j % STAGES;
+    TileD d;
+    if (FEAT & 2) { d = dnext; if (j + 1 < mine) dnext = tiles[first + (j + 1) * stride]; }
+    else { const int t = first + j * stride; d = TileD{t * ROWS, ROWS, t * TILE, TILE}; }
+    sdesc[slot] = d;
+    const int s_al = d.s & ~3, cnt = (d.n + (d.s - s_al) + 3) & ~3;
+    const int r_al = d.r0 & ~3, rcnt = (d.nrows + 1 + (d.r0 - r_al) + 3) & ~3;
+    mbar_expect(&full[slot], (uint32_t)(cnt * 12 + ((FEAT & 1) ? rcnt * 4 : 0)));
+    if (FEAT & 4) {
+      tma1d_pol(st[slot].v, val + s_al, cnt * 8, &full[slot], pol);
+      tma1d_pol(st[slot].c, col + s_al, cnt * 4, &full[slot], pol);
+      if (FEAT & 1) tma1d_pol(st[slot].r, rp + r_al, rcnt * 4, &full[slot], pol);
+    } else {
+      tma1d(st[slot].v, val + s_al, cnt * 8, &full[slot]);
+      tma1d(st[slot].c, col + s_al, cnt * 4, &full[slot]);
+      if (FEAT & 1) tma1d(st[slot].r, rp + r_al, rcnt * 4, &full[slot]);
+    }
+  };
+  if (tid == 0) for (int j = 0; j < STAGES - 1 && j < mine; ++j) issue(j);
+  __syncthreads();
+  for (int it = 0; it < mine; ++it) {
+    const int slot = it % STAGES;
+    const TileD d = sdesc[slot];
+    Stage &S = st[slot];
+    constexpr int RPT = (ROWS + NT - 1) / NT;
+    double bi[RPT], pD[RPT], pout[RPT];
+#pragma unroll
+    for (int r0 = 0; r0 < RPT; ++r0) {
+      const int r = tid + r0 * NT;
+      bi[r0] = 0.0; pD[r0] = 1.0; pout[r0] = 0.0;
+      if (r < d.nrows) {
+        if (FEAT & 8) {
+          bi[r0] = ge.aux ? ge.aux[d.r0 + r] : 0.0;
+          pD[r0] = ge.D ? ge.D[d.r0 + r] : 1.0;
+          pout[r0] = ge.out_mode == 2 ? ge.out[d.r0 + r] : 0.0;
+        } else {
+          bi[r0] = b[d.r0 + r];
+        }
+      }
+    }
+    mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
+    const int o = d.s & 3;
+    double xr[TILE / NT];
+#pragma unroll
+    for (int k0 = 0; k0 < TILE / NT; ++k0) { const int k = tid + k0 * NT; xr[k0] = 0.0; if (k < d.n) xr[k0] = x[S.c[o + k]]; }
+    if (tid == 0 && it + STAGES - 1 < mine) issue(it + STAGES - 1);
+#pragma unroll
+    for (int k0 = 0; k0 < TILE / NT; ++k0) { const int k = tid + k0 * NT; if (k < d.n) S.v[o + k] *= xr[k0]; }
+    __syncthreads();
+    const int ro = d.r0 & 3;
+#pragma unroll
+    for (int r0 = 0; r0 < RPT; ++r0) {
+      const int r = tid + r0 * NT;
+      if (r < d.nrows) {
+        double s = 0.0;
+        if (FEAT & 1) {
+          int p = S.r[ro + r] - d.s + o;
+          const int q = S.r[ro + r + 1] - d.s + o;
+          for (; p < q; ++p) s += S.v[p];
+        } else {
+#pragma unroll
+          for (int k = 0; k < L; ++k) s += S.v[o + r * L + k];
+        }
+        const int i = d.r0 + r;
+        if (FEAT & 8) {
+          if (ge.D) s = s / pD[r0];
+          if (ge.neumann) s = ge.x[i] - s;
+          double v = ge.beta * s;
+          if (ge.aux) v = ge.alpha * bi[r0] + v;
+          if (ge.wout) { double xw = 0.0; for (int q2 = 0; q2 < ge.fd_its; ++q2) xw = xw + ge.fd_m[i] * (v - ge.fd_a[i] * xw); ge.wout[i] = xw; }
+          if (ge.out_mode == 1) ge.out[i] = v;
+          else if (ge.out_mode == 2) ge.out[i] = pout[r0] + v;
+          if (ge.out2) ge.out2[i] = ge.delta * v;
+          if (ge.acc_mode) { const double t2 = ge.gamma * (ge.acc_src ? ge.acc_src[i] : v); if (ge.acc_mode == 1) ge.acc[i] = t2; else ge.acc[i] += t2; }
+        } else {
+          y[i] = bi[r0] - s;
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ V2
 // NT threads = 1 producer warp + (NT/32 - 1) consumer warps.  Ring of R slots.
 template <int NT, int TILE, int R, int G, int L>
@@ -178,6 +297,8 @@ float time_kernel(K launch) {
   return ms / 5;
 }
 
+static bool bisect = false;
+
 template <int L>
 void run(int n, int spread) {
   const size_t nnz = (size_t)n * L;
@@ -226,6 +347,25 @@ void run(int n, int spread) {
     if (nb >= 1) { const int cps = nb < CPS ? nb : CPS; float ms = time_kernel([&] { spmv_v2<NT, TILE, R, G, L><<<148 * cps, NT, sm>>>(val, col, x, b, y, ntiles); }); \
     char nm[96]; snprintf(nm, 96, "V2 NT%d T%d R%d G%d CTAs/SM %d", NT, TILE, R, G, cps); check(nm, ms); } } }
   RUN_V0(256, 1024, 2, 3) RUN_V0(256, 1024, 3, 4) RUN_V0(256, 2048, 3, 3)
+  if (bisect) {
+    constexpr int TILE = 1024, NT = 256, S = 2;
+    const int ntiles = (int)(nnz / TILE);
+    std::vector<int> hrp((size_t)n + 9);
+    for (int i = 0; i <= n; ++i) hrp[i] = i * L;
+    std::vector<TileD> ht((size_t)ntiles);
+    for (int t = 0; t < ntiles; ++t) ht[t] = TileD{t * (TILE / L), TILE / L, t * TILE, TILE};
+    int *rp; TileD *tiles;
+    CK(cudaMalloc(&rp, hrp.size() * 4)); CK(cudaMalloc(&tiles, ht.size() * sizeof(TileD)));
+    CK(cudaMemcpy(rp, hrp.data(), hrp.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(tiles, ht.data(), ht.size() * sizeof(TileD), cudaMemcpyHostToDevice));
+    GenEpi ge{}; ge.aux = b; ge.alpha = 1.0; ge.beta = -1.0; ge.out = y; ge.out_mode = 1; ge.x = x;
+    const size_t sm = (size_t)S * ((TILE + 8) * 12 + (TILE / L + 8) * 4 + 64);
+#define RUN_F(FEAT) { CK(cudaFuncSetAttribute(spmv_v0f<NT, TILE, S, L, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+      int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmv_v0f<NT, TILE, S, L, FEAT>, NT, sm); const int cps = nb < 3 ? nb : 3; \
+      float ms = time_kernel([&] { spmv_v0f<NT, TILE, S, L, FEAT><<<148 * cps, NT, sm>>>(val, col, rp, tiles, x, b, y, ntiles, ge); }); \
+      char nm[96]; snprintf(nm, 96, "V0F feat %2d CTAs/SM %d (occ %d)", FEAT, cps, nb); check(nm, ms); }
+    RUN_F(0) RUN_F(1) RUN_F(2) RUN_F(4) RUN_F(8) RUN_F(3) RUN_F(7) RUN_F(11) RUN_F(15)
+    cudaFree(rp); cudaFree(tiles);
+  }
   RUN_V2(256, 1024, 4, 2, 8) RUN_V2(256, 1024, 6, 3, 8) RUN_V2(256, 1024, 8, 4, 8)
   RUN_V2(256, 2048, 4, 2, 8) RUN_V2(256, 2048, 5, 2, 8)
   RUN_V2(128, 1024, 4, 2, 8) RUN_V2(128, 1024, 6, 3, 8) RUN_V2(128, 512, 6, 3, 8) RUN_V2(128, 512, 8, 4, 8)
@@ -267,7 +407,8 @@ void launch_overhead() {
 }
 
 int main(int argc, char **argv) {
-  if (argc > 1) { launch_overhead(); return 0; }
+  if (argc > 1 && argv[1][0] == 'o') { launch_overhead(); return 0; }
+  if (argc > 1 && argv[1][0] == 'b') bisect = true;
   const int n = 1 << 24;
   run<2>(n, 3000);
   run<8>(n / 2, 3000);
