@@ -138,3 +138,16 @@ def test_problem_generators_match_reference_stencils():
     assert np.isclose(row[(j - 1) * n + i], -v) and np.isclose(row[j * n + i - 1], -u) and np.isclose(row[j * n + i], u + v)
     assert A[0, 0] == 1.0 and A[0].nnz == 1                       # inflow row = identity
     assert A.nnz == (n - 1) * (n - 1) * 3 + (2 * n - 1)
+
+
+def test_c_abi_from_plain_c(built_libs, tmp_path):
+    """include/pflare_b200.h compiles as C99 and the library can be driven from C (host-only planning context):
+    the language and calling convention of the reference's FFI layer (src/C_PETSc_Routines.c)."""
+    import subprocess
+    exe = str(tmp_path / "capi_host_check")
+    libdir = os.path.dirname(pflare_b200.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "c", "capi_host_check.c"), "-L", libdir, "-lpflare_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "CAPI_HOST_OK" in out.stdout, out.stdout + out.stderr
