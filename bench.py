@@ -423,7 +423,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PFLARE_BENCH_WORKLOAD", "adv_diff_fd_2d"))
     ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("PFLARE_BENCH_N", "4096")))
-    ap.add_argument("--cpu-cycles", type=int, default=5)
+    ap.add_argument("--cpu-cycles", type=int, default=20)
     ap.add_argument("--ref-max-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
