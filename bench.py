@@ -374,8 +374,16 @@ def run_gpu(args):
         "largest_launch": {"bytes": biggest[0], "ms": biggest[1], "level": biggest[2],
                            "GBps": biggest[0] / (biggest[1] * 1e-3) / 1e9 if biggest[1] > 0 else None},
         "algorithmic_bytes_per_cycle": st["algorithmic_bytes"], "nnz_per_cycle": st["nnz_per_cycle"],
-        "traffic_note": "ncu --set full (profiles/): dram__bytes of the SpMV launches = 0.93-1.0 x their algorithmic bytes",
     }
+    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of this same workload
+    # (profiles/r01_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per captured launch)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        roof["traffic"] = tr["mean_dram_bytes_per_launch"]
+        roof["traffic_detail"] = {"launches": len(tr["launches"]), "mean_algorithmic_bytes_per_launch": tr["mean_algorithmic_bytes_per_launch"],
+                                  "dram_over_algorithmic": tr["dram_over_algorithmic"], "source": tr["source"]}
+    except Exception:
+        pass
 
     # whole-job counters (bytes / launches summed over the ranks)
     tot = torch.tensor([st["algorithmic_bytes"], st["kernel_launches"], st["ghost_bytes_sent"], st["device_bytes"]], device="cuda", dtype=torch.float64)
