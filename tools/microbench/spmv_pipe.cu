@@ -406,8 +406,62 @@ void launch_overhead() {
   }
 }
 
+// real operator from a file written by dump_operator.py: int64 n, int64 nnz, int32 rp[n+1], int32 col[nnz], double val[nnz]
+// (square, rows <= 1024 nonzeros).  Runs the scalar kernel and the V0F kernels with run-time tiles (<= 1024 nnz, <= 256 rows).
+void run_real(const char *path) {
+  FILE *f = fopen(path, "rb");
+  if (!f) { printf("cannot open %s\n", path); return; }
+  long long n64, nnz64;
+  if (fread(&n64, 8, 1, f) != 1 || fread(&nnz64, 8, 1, f) != 1) { printf("bad header\n"); return; }
+  const int n = (int)n64; const size_t nnz = (size_t)nnz64;
+  std::vector<int> hrp((size_t)n + 9, 0), hc(nnz + 8, 0); std::vector<double> hv(nnz + 8, 0.0);
+  if (fread(hrp.data(), 4, (size_t)n + 1, f) != (size_t)n + 1 || fread(hc.data(), 4, nnz, f) != nnz || fread(hv.data(), 8, nnz, f) != nnz) { printf("short file\n"); return; }
+  fclose(f);
+  for (int i = n + 1; i < n + 9; ++i) hrp[i] = hrp[n];
+  constexpr int TILE = 1024, NT = 256, S = 2, L = 4;     // L = 4 only sizes the stage for 256 rows
+  std::vector<TileD> ht;
+  for (int r = 0; r < n;) {
+    int r0 = r; const int base = hrp[r0];
+    if (hrp[r0 + 1] - base > TILE) { printf("row %d longer than a tile: not supported here\n", r0); return; }
+    while (r < n && r - r0 < TILE / L && hrp[r + 1] - base <= TILE) ++r;
+    ht.push_back(TileD{r0, r - r0, base, hrp[r] - base});
+  }
+  const int ntiles = (int)ht.size();
+  std::vector<double> hx(n), hb(n);
+  srand(2);
+  for (int i = 0; i < n; ++i) { hx[i] = (rand() % 1000) / 1000.0; hb[i] = (rand() % 1000) / 500.0; }
+  double *val, *x, *b, *y, *yref; int *col, *rp; TileD *tiles;
+  CK(cudaMalloc(&val, (nnz + 8) * 8)); CK(cudaMalloc(&col, (nnz + 8) * 4)); CK(cudaMalloc(&rp, hrp.size() * 4)); CK(cudaMalloc(&tiles, ht.size() * sizeof(TileD)));
+  CK(cudaMalloc(&x, (size_t)n * 8 + 64)); CK(cudaMalloc(&b, (size_t)n * 8 + 64)); CK(cudaMalloc(&y, (size_t)n * 8 + 64)); CK(cudaMalloc(&yref, (size_t)n * 8 + 64));
+  CK(cudaMemcpy(val, hv.data(), (nnz + 8) * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(col, hc.data(), (nnz + 8) * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(rp, hrp.data(), hrp.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(tiles, ht.data(), ht.size() * sizeof(TileD), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(x, hx.data(), (size_t)n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(b, hb.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+  // reference result on the host
+  std::vector<double> href(n), hy(n);
+  for (int i = 0; i < n; ++i) { double sacc = 0; for (int p = hrp[i]; p < hrp[i + 1]; ++p) sacc += hv[p] * hx[hc[p]]; href[i] = hb[i] - sacc; }
+  const double bytes = 12.0 * nnz + 4.0 * n + 24.0 * n;
+  printf("%s: n %d nnz %zu (%.2f per row), %d tiles\n", path, n, nnz, (double)nnz / n, ntiles);
+  auto check = [&](const char *name, float ms) {
+    CK(cudaMemcpy(hy.data(), y, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    double err = 0;
+    for (int i = 0; i < n; ++i) err = fmax(err, fabs(hy[i] - href[i]));
+    printf("  %-34s %8.3f ms  %7.0f GB/s   maxerr %.1e\n", name, ms, bytes / (ms * 1e-3) / 1e9, err);
+    CK(cudaMemset(y, 0, (size_t)n * 8));
+  };
+  GenEpi ge{}; ge.aux = b; ge.alpha = 1.0; ge.beta = -1.0; ge.out = y; ge.out_mode = 1; ge.x = x;
+  const size_t sm = (size_t)S * ((TILE + 8) * 12 + (TILE / L + 8) * 4 + 64);
+#define RUN_R(FEAT) { CK(cudaFuncSetAttribute(spmv_v0f<NT, TILE, S, L, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, spmv_v0f<NT, TILE, S, L, FEAT>, NT, sm); const int cps = nb < 3 ? nb : 3; \
+    const int grid = ntiles < 148 * cps ? ntiles : 148 * cps; \
+    float ms = time_kernel([&] { spmv_v0f<NT, TILE, S, L, FEAT><<<grid, NT, sm>>>(val, col, rp, tiles, x, b, y, ntiles, ge); }); \
+    char nm[96]; snprintf(nm, 96, "V0F feat %2d CTAs/SM %d", FEAT, cps); check(nm, ms); }
+  RUN_R(3) RUN_R(7) RUN_R(11) RUN_R(15)
+  cudaFree(val); cudaFree(col); cudaFree(rp); cudaFree(tiles); cudaFree(x); cudaFree(b); cudaFree(y); cudaFree(yref);
+}
+
 int main(int argc, char **argv) {
   if (argc > 1 && argv[1][0] == 'o') { launch_overhead(); return 0; }
+  if (argc > 2 && argv[1][0] == 'r') { for (int a = 2; a < argc; ++a) run_real(argv[a]); return 0; }
   if (argc > 1 && argv[1][0] == 'b') bisect = true;
   const int n = 1 << 24;
   run<2>(n, 3000);
