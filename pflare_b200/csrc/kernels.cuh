@@ -4,37 +4,57 @@
 // (SURVEY.md section 2c): the CSR product of a row is reduced once and the row epilogue applies
 // the fused vector updates.  The path is HBM-bound fp64/int32 work (no tensor cores by design).
 //
-//   spmv_tma_kernel     the kernel of the large levels: persistent CTAs, the matrix stream
-//                       (values, column indices, row pointers of a tile) is brought into a
-//                       shared-memory ring by 1-D TMA bulk copies signalled on mbarriers, so the
-//                       HBM stream never drains while a tile is multiplied / reduced; the
-//                       per-row epilogue operands are prefetched into registers before the
-//                       tile's barrier is waited on.
-//   spmv_stream_kernel  the first-generation smem-staged kernel (option kernel=0; A/B baseline).
-//   tail_kernel         single CTA that runs the whole list of ops of the small coarse levels
-//                       back to back with CTA barriers instead of kernel launches.
+//   spmv_wt_kernel      the kernel of the cycle (round 2).  The operator is stored as WARP TILES: one
+//                       contiguous blob per tile (<= 256 nonzeros of consecutive rows: values, column
+//                       indices, per-lane row-end masks) that ONE 1-D TMA bulk copy brings into a
+//                       per-warp shared-memory ring.  Warps are autonomous (no CTA barrier anywhere):
+//                       while a warp reduces tile t its x gathers and epilogue operands of tile t+1 are
+//                       already in flight in registers and tiles t+2.. are in flight in the ring.  Rows
+//                       are summed by a lane-local walk plus one segmented warp scan; the row epilogue
+//                       is specialised at compile time per op class.
+//   spmv_tma_kernel     round-1 kernel (CTA tiles of a CSR stream, 3 bulk copies per tile, CTA barriers);
+//                       kept as option kernel=1 for A/B measurements.
+//   spmv_stream_kernel  first-generation smem-staged kernel (option kernel=0); also the fallback for
+//                       operators with rows longer than a warp tile.
 //   ew_kernel           diagonal inverses / scalings / permutations.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "wt_format.h"
+
 namespace pfb {
 
 constexpr int kThreads = 256;       // CTA size of the streaming kernels
-constexpr int kTile = 2048;         // nnz per CTA tile of the stream / tail kernels (16 KB of fp64 products)
+constexpr int kTile = 2048;         // nnz per CTA tile of the stream kernel (16 KB of fp64 products)
 constexpr int kMaxRowsPerBlk = 1024;
-constexpr int kTailThreads = 1024;  // CTA size of the single-CTA tail kernel
 
 struct TileDesc { int r0, nrows, s, n; };  // first row, #rows, first nnz, #nnz (n > tile size: one long row)
 
+// epilogue classes of the warp-tile kernel (compile-time specialisations of the row epilogue)
+enum { EPI_GENERIC = 0,     // everything below, decided at run time
+       EPI_ADD = 1,         // out[i] += s                         restriction b_c += Z b_f ; x_f += M r
+       EPI_SET = 2,         // out[i]  = s                         coarse solve, PCPFLAREINV, x_f = W x_c
+       EPI_AXPBY = 3,       // out[i]  = alpha aux[i] + beta s     residuals, Horner steps
+       EPI_AFCW = 4,        // merged A_fc|W: out = aux - s ; wout = w x_c
+       EPI_AFCW_LOCAL = 5,  // merged A_fc|W + row-local F smooth (diagonal A_ff and M_ff)
+       EPI_AXPBY_ACC = 6,   // Newton-basis steps: out = alpha aux + beta s ; acc (=|+=) gamma (acc_src | out)
+       EPI_NCLASS = 7 };
+
 struct SpmvOp {
-  // CSR block + its row-block partition
+  // CSR block + its row-block partition (kernel 0 / 1 and the long-row fallback)
   const int *rp, *col;
   const double *val;
   int m, nblk;
   const int *blk;
-  const TileDesc *tiles;       // tile list of the TMA-pipelined kernel
+  const TileDesc *tiles;       // tile list of the round-1 TMA kernel
   int ntiles;
+  // warp-tile storage (kernel 2)
+  const unsigned char *blob;
+  const WtDesc *wdesc;
+  int nwt;
+  int rq;                      // rows per lane of a tile: a tile holds <= 32 * rq rows
+  int epi;                     // epilogue class
   // gather sources: column c < nloc reads x[c], otherwise xg[c - nloc] (ghost buffer)
   const double *x, *xg;
   int nloc;
@@ -53,13 +73,13 @@ struct SpmvOp {
   // fully local F smooth (diagonal A_ff and diagonal inverse): x = wout value; repeat fd_its:
   // x += fd_m[i] * (v - fd_a[i] * x); wout[i] = x
   const double *fd_a, *fd_m; int fd_its;
+  // entry / exit permutation of the cycle fused into the level-1 ops (natural <-> nested ordering):
+  //   aux_idx  : aux is read as aux[aux_idx[i]]          (b in PETSc's natural ordering)
+  //   wout_idx : wout / out is ALSO stored to xnat[wout_idx[i]]  (x in natural ordering)
+  const int *aux_idx; const int *wout_idx; double *xnat;
   // peer-memory ghost exchange: before the first ghost read, wait until every source rank has pushed
   // its chunk of THIS exchange instance (ready[q] >= *epoch for the ranks q in srcmask)
   const unsigned *gw_ready; const unsigned *gw_epoch; unsigned gw_srcmask;
-  // wide-tile kernel: up to 3 epilogue operand arrays travel with the tile as TMA bulk copies
-  // (field ids: 1 aux, 2 D, 3 x_i (Neumann), 4 fd_a, 5 fd_m, 6 out (read-modify-write), 7 acc_src, 8 acc)
-  unsigned char stg_field[3]; unsigned char n_stg; unsigned stg_mask;
-  int wide;                    // this operator's tile list was built for spmv_tma_wide_kernel
 };
 
 // out[i] (=|+=) alpha * a[i] * (b ? b[i] : 1) / (dv ? dv[i] : 1)
@@ -70,12 +90,6 @@ struct EwOp {
   double *out; int mode;  // 1 set, 2 add
   const int *gather;      // optional: read a[gather[i]]
   const int *scatter;     // optional: write out[scatter[i]]
-};
-
-struct DevOp {
-  int kind;  // 0 spmv, 1 elementwise
-  SpmvOp s;
-  EwOp e;
 };
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
@@ -94,7 +108,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// consumer side: called by ONE thread of a CTA before the CTA's first ghost read
+// consumer side: called by ONE thread of a CTA (or warp) before its first ghost read
 __device__ __forceinline__ void ghost_wait(const unsigned *ready, const unsigned *epoch, unsigned srcmask) {
   if (!ready) return;
   const unsigned e = *epoch;
@@ -112,13 +126,13 @@ __device__ __forceinline__ double gather_x(const SpmvOp &op, int c) {
   return op.x[c];
 }
 
-// Row epilogue, split in two so that the loads that depend only on the row index can be issued
-// long before the row sum exists.
+// ---- generic (run-time branched) row epilogue, split in two so that the loads that depend only on
+// the row index can be issued long before the row sum exists
 struct EpiPre { double aux, D, xi, fa, fm, out, accsrc, acc; };
 
 __device__ __forceinline__ EpiPre epi_prefetch(const SpmvOp &op, int i) {
   EpiPre p;
-  p.aux = op.aux ? op.aux[i] : 0.0;
+  p.aux = op.aux ? op.aux[op.aux_idx ? op.aux_idx[i] : i] : 0.0;
   p.D = op.D ? op.D[i] : 1.0;
   p.xi = op.neumann ? op.x[i] : 0.0;
   p.fa = op.fd_its > 0 ? op.fd_a[i] : 0.0;
@@ -129,44 +143,6 @@ __device__ __forceinline__ EpiPre epi_prefetch(const SpmvOp &op, int i) {
   return p;
 }
 
-__device__ __forceinline__ const double *epi_field_ptr(const SpmvOp &op, int f) {
-  switch (f) {
-    case 1: return op.aux;
-    case 2: return op.D;
-    case 3: return op.x;
-    case 4: return op.fd_a;
-    case 5: return op.fd_m;
-    case 6: return op.out;
-    case 7: return op.acc_src;
-    default: return op.acc;
-  }
-}
-// epi_prefetch for the fields that were NOT staged (mask bit f-1 set = staged)
-__device__ __forceinline__ EpiPre epi_prefetch_masked(const SpmvOp &op, int i, unsigned m) {
-  EpiPre p;
-  p.aux = (op.aux && !(m & 1u)) ? op.aux[i] : 0.0;
-  p.D = (op.D && !(m & 2u)) ? op.D[i] : 1.0;
-  p.xi = (op.neumann && !(m & 4u)) ? op.x[i] : 0.0;
-  p.fa = (op.fd_its > 0 && !(m & 8u)) ? op.fd_a[i] : 0.0;
-  p.fm = (op.fd_its > 0 && !(m & 16u)) ? op.fd_m[i] : 0.0;
-  p.out = (op.out_mode == 2 && !(m & 32u)) ? op.out[i] : 0.0;
-  p.accsrc = (op.acc_mode && op.acc_src && !(m & 64u)) ? op.acc_src[i] : 0.0;
-  p.acc = (op.acc_mode == 2 && !(m & 128u)) ? op.acc[i] : 0.0;
-  return p;
-}
-__device__ __forceinline__ void epi_set_field(EpiPre &p, int f, double v) {
-  switch (f) {
-    case 1: p.aux = v; break;
-    case 2: p.D = v; break;
-    case 3: p.xi = v; break;
-    case 4: p.fa = v; break;
-    case 5: p.fm = v; break;
-    case 6: p.out = v; break;
-    case 7: p.accsrc = v; break;
-    default: p.acc = v; break;
-  }
-}
-
 __device__ __forceinline__ void epi_finish(const SpmvOp &op, int i, double s, double xw, const EpiPre &p) {
   if (op.D) s = s / p.D;
   if (op.neumann) s = p.xi - s;
@@ -175,6 +151,7 @@ __device__ __forceinline__ void epi_finish(const SpmvOp &op, int i, double s, do
   if (op.wout) {
     for (int it = 0; it < op.fd_its; ++it) xw = xw + p.fm * (v - p.fa * xw);
     op.wout[i] = xw;
+    if (op.wout_idx) op.xnat[op.wout_idx[i]] = xw;
   }
   if (op.out_mode == 1) op.out[i] = v;
   else if (op.out_mode == 2) op.out[i] = p.out + v;
@@ -189,6 +166,74 @@ __device__ __forceinline__ void row_epilogue(const SpmvOp &op, int i, double s, 
   const EpiPre p = epi_prefetch(op, i);
   epi_finish(op, i, s, xw, p);
 }
+
+// ---- compile-time epilogue classes: Pre = the operands prefetched per row (one tile ahead)
+template <int EPI> struct EpiT;
+template <> struct EpiT<EPI_GENERIC> {
+  static constexpr int kPre = 0; static constexpr bool kXw = true;
+  struct Pre {};
+  static __device__ __forceinline__ Pre prefetch(const SpmvOp &, int) { return Pre(); }
+  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double xw, const Pre &) { row_epilogue(op, i, s, xw); }
+};
+template <> struct EpiT<EPI_ADD> {
+  static constexpr int kPre = 1; static constexpr bool kXw = false;
+  struct Pre { double o; };
+  static __device__ __forceinline__ Pre prefetch(const SpmvOp &op, int i) { Pre p; p.o = op.out[i]; return p; }
+  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double, const Pre &p) { op.out[i] = p.o + s; }
+};
+template <> struct EpiT<EPI_SET> {
+  static constexpr int kPre = 0; static constexpr bool kXw = false;
+  struct Pre {};
+  static __device__ __forceinline__ Pre prefetch(const SpmvOp &, int) { return Pre(); }
+  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double, const Pre &) { op.out[i] = s; }
+};
+template <> struct EpiT<EPI_AXPBY> {
+  static constexpr int kPre = 1; static constexpr bool kXw = false;
+  struct Pre { double a; };
+  static __device__ __forceinline__ Pre prefetch(const SpmvOp &op, int i) { Pre p; p.a = op.aux[op.aux_idx ? op.aux_idx[i] : i]; return p; }
+  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double, const Pre &p) {
+    const double v = op.beta * s;
+    op.out[i] = op.alpha * p.a + v;
+  }
+};
+template <> struct EpiT<EPI_AFCW> {
+  static constexpr int kPre = 1; static constexpr bool kXw = true;
+  struct Pre { double a; };
+  static __device__ __forceinline__ Pre prefetch(const SpmvOp &op, int i) { Pre p; p.a = op.aux[op.aux_idx ? op.aux_idx[i] : i]; return p; }
+  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double xw, const Pre &p) {
+    const double v = op.beta * s;
+    op.wout[i] = xw;
+    op.out[i] = op.alpha * p.a + v;
+  }
+};
+template <> struct EpiT<EPI_AFCW_LOCAL> {
+  static constexpr int kPre = 3; static constexpr bool kXw = true;
+  struct Pre { double a, fa, fm; };
+  static __device__ __forceinline__ Pre prefetch(const SpmvOp &op, int i) {
+    Pre p; p.a = op.aux[op.aux_idx ? op.aux_idx[i] : i]; p.fa = op.fd_a[i]; p.fm = op.fd_m[i]; return p;
+  }
+  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double xw, const Pre &p) {
+    double v = op.beta * s;
+    v = op.alpha * p.a + v;
+    for (int it = 0; it < op.fd_its; ++it) xw = xw + p.fm * (v - p.fa * xw);
+    op.wout[i] = xw;
+    if (op.wout_idx) op.xnat[op.wout_idx[i]] = xw;
+  }
+};
+template <> struct EpiT<EPI_AXPBY_ACC> {
+  static constexpr int kPre = 3; static constexpr bool kXw = false;
+  struct Pre { double a, as, ac; };
+  static __device__ __forceinline__ Pre prefetch(const SpmvOp &op, int i) {
+    Pre p; p.a = op.aux[i]; p.as = op.acc_src ? op.acc_src[i] : 0.0; p.ac = op.acc_mode == 2 ? op.acc[i] : 0.0; return p;
+  }
+  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double, const Pre &p) {
+    double v = op.beta * s;
+    v = op.alpha * p.a + v;
+    op.out[i] = v;
+    const double t = op.gamma * (op.acc_src ? p.as : v);
+    op.acc[i] = op.acc_mode == 1 ? t : p.ac + t;
+  }
+};
 
 // Process one row block with all threads of the CTA.  `prod` holds kTile doubles.
 template <int NT>
@@ -250,21 +295,7 @@ __global__ void __launch_bounds__(kThreads) spmv_stream_kernel(const SpmvOp op) 
 }
 
 // ------------------------------------------------------------------------------------------
-// TMA-pipelined streaming SpMV (the kernel of the large levels).
-//
-// A persistent CTA walks its tiles (tile = consecutive rows holding <= TILE nonzeros and <= NT
-// rows, fixed at upload).  For every tile ONE elected thread issues three 1-D bulk copies
-// (cp.async.bulk, the TMA engine: SASS UBLKCP) that bring the tile's values, column indices and
-// row pointers into a STAGES-deep shared-memory ring; completion is signalled on an mbarrier per
-// stage.  While tile t is being multiplied/reduced, tiles t+1 .. t+STAGES-1 are in flight, so the
-// HBM stream does not drain at the barriers of the multiply/reduce phases.  Every thread owns at
-// most one row of the tile and issues the loads of that row's epilogue operands BEFORE it waits
-// for the tile, so the reduce phase touches no global-memory latency.  x is gathered with
-// ordinary loads (L1/L2; the nested CF ordering keeps the gathers near-sequential).
-//
-// Bulk copies need 16-byte aligned addresses and sizes: the copy starts at the tile's first
-// nonzero rounded DOWN to a multiple of 4 entries and is rounded UP to a multiple of 4 (the
-// arrays are over-allocated by a few entries at upload).
+// mbarrier / TMA (1-D bulk copy) helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -299,6 +330,173 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-tile SpMV (the kernel of the cycle).
+//
+// Persistent CTAs of NW autonomous warps.  Global warp g owns the tiles g, g + #warps, ...; lane 0
+// keeps STAGES bulk copies (one per tile) in flight into the warp's private ring, each signalled on
+// its own mbarrier.  Per tile the warp runs two software-pipelined stages:
+//   A (one tile ahead)  read the tile's column indices from shared memory and issue the x gathers
+//                       and the loads of the rows' epilogue operands into registers;
+//   B                   products in registers; every lane walks its kpl consecutive nonzeros, a
+//                       segmented warp scan (shuffles) carries the partial sum of a row that spans
+//                       lanes; finished row sums go to shared memory (the consumed value area of the
+//                       stage) so that the epilogue runs with one row per lane (coalesced vector
+//                       traffic), RQ rows per lane for operators with short rows.
+// No __syncthreads: a warp never waits for another warp, so one warp's gather latency is hidden by
+// the other warps of the SM and the bulk stream never drains.
+template <int EPI, int RQ, bool GHOST, int NW, int STAGES>
+__global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
+  typedef EpiT<EPI> E;
+  typedef typename E::Pre Pre;
+  constexpr bool XW = E::kXw;
+  constexpr int KPL = kWtKpl;
+  constexpr bool AHEAD = E::kPre * RQ <= 16;   // epilogue operands prefetched one tile ahead (else at the start of stage B)
+  constexpr int XW_BYTES = XW ? RQ * 32 * 8 : 0;
+  constexpr int WARP_BYTES = STAGES * kWtStageBytes + XW_BYTES;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[NW][STAGES];
+  __shared__ WtDesc sdesc[NW][STAGES];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned char *wbase = smem_raw + (size_t)w * WARP_BYTES;
+  double *xw_s = reinterpret_cast<double *>(wbase + STAGES * kWtStageBytes);
+  const int nwarps = gridDim.x * NW;
+  const int first = blockIdx.x * NW + w;
+  const int my = first < op.nwt ? (op.nwt - first + nwarps - 1) / nwarps : 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[w][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint64_t pol = l2_policy_evict_first();
+  const WtDesc *__restrict__ wdesc = op.wdesc;
+  // producer (lane 0): one bulk copy per tile; the descriptor of the NEXT tile is fetched one issue ahead
+  WtDesc dn = {0u, 0, 0, 0};
+  if (lane == 0 && my > 0) dn = wdesc[first];
+  auto issue = [&](int j) {
+    const WtDesc d = dn;
+    if (j + 1 < my) dn = wdesc[(size_t)first + (size_t)(j + 1) * nwarps];
+    const int slot = j % STAGES;
+    sdesc[w][slot] = d;
+    const uint32_t bytes = (uint32_t)(d.kpl * 384 + 64);
+    mbar_expect_tx(&full[w][slot], bytes);
+    tma_load_1d(wbase + slot * kWtStageBytes, op.blob + (size_t)d.off16 * 16, bytes, &full[w][slot], pol);
+  };
+  pdl_launch_dependents();
+  if (lane == 0)
+    for (int j = 0; j < STAGES && j < my; ++j) issue(j);   // matrix data only: legal before pdl_wait
+  pdl_wait();   // from here on the vectors written by the previous kernels are read
+  if (GHOST && lane == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+  __syncwarp();
+
+  const double *__restrict__ xv = op.x;
+  const double *__restrict__ xg = op.xg;
+  const int nloc = op.nloc;
+  WtDesc dnx = {0u, 0, 0, 0};
+  double xn[KPL];
+  Pre pn[RQ];
+  // stage A of tile j
+  auto stage_a = [&](int j) {
+    const int slot = j % STAGES;
+    mbar_wait(&full[w][slot], (uint32_t)((j / STAGES) & 1));
+    dnx = sdesc[w][slot];
+    const int *col_s = reinterpret_cast<const int *>(wbase + slot * kWtStageBytes + dnx.kpl * 256);
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      xn[k] = 0.0;
+      if (k < dnx.kpl) {
+        const int c = col_s[k * 32 + lane];
+        if (GHOST) xn[k] = (c >= nloc) ? __ldcg(xg + (c - nloc)) : xv[c];
+        else xn[k] = xv[c];
+      }
+    }
+    if (AHEAD) {
+#pragma unroll
+      for (int q = 0; q < RQ; ++q)
+        if (lane + 32 * q < dnx.nrows) pn[q] = E::prefetch(op, dnx.r0 + lane + 32 * q);
+    }
+  };
+  if (my > 0) stage_a(0);
+  for (int it = 0; it < my; ++it) {
+    const WtDesc d = dnx;
+    double p[KPL];
+    Pre pc[RQ];
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) p[k] = xn[k];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) pc[q] = pn[q];
+    if (it + 1 < my) stage_a(it + 1);
+    // ---- stage B
+    const int slot = it % STAGES;
+    unsigned char *st = wbase + slot * kWtStageBytes;
+    double *val_s = reinterpret_cast<double *>(st);
+    if (!AHEAD) {
+#pragma unroll
+      for (int q = 0; q < RQ; ++q)
+        if (lane + 32 * q < d.nrows) pc[q] = E::prefetch(op, d.r0 + lane + 32 * q);
+    }
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) p[k] = (k < d.kpl) ? val_s[k * 32 + lane] * p[k] : 0.0;
+    const unsigned e = reinterpret_cast<const unsigned short *>(st + d.kpl * 384)[lane];
+    __syncwarp();   // every lane holds its values: the value area now receives the row sums
+    // partial sum after this lane's last row end (the whole lane if it ends no row)
+    const int last = 31 - __clz((int)e);
+    double tail = 0.0;
+#pragma unroll
+    for (int k = 0; k < KPL; ++k)
+      if (k > last) tail += p[k];
+    // segmented inclusive scan of the tails over the lanes (a lane that ends a row starts a new segment)
+    const unsigned has = __ballot_sync(0xffffffffu, e != 0u);
+    const unsigned upto = has & (0xffffffffu >> (31 - lane));
+    const int dist = lane - (upto ? 31 - __clz((int)upto) : 0);
+    double sc = tail;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, sc, o);
+      if (o <= dist) sc += t;
+    }
+    double acc = __shfl_up_sync(0xffffffffu, sc, 1);   // the open row's partial sum entering this lane
+    if (lane == 0) acc = 0.0;
+    // first tile-local row index this lane finishes
+    const int cnt = __popc(e);
+    int rb = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, rb, o);
+      if (lane >= o) rb += t;
+    }
+    rb -= cnt;
+    const bool wl = (EPI == EPI_AFCW || EPI == EPI_AFCW_LOCAL) || (EPI == EPI_GENERIC && op.wlast);
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const bool end = (e >> k) & 1u;
+      if (XW && wl) {
+        if (end) { val_s[rb] = acc; xw_s[rb] = p[k]; ++rb; acc = 0.0; }
+        else acc += p[k];
+      } else {
+        acc += p[k];
+        if (end) { val_s[rb] = acc; ++rb; acc = 0.0; }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+      const int r = lane + 32 * q;
+      if (r < d.nrows) E::finish(op, d.r0 + r, val_s[r], (XW && wl) ? xw_s[r] : 0.0, pc[q]);
+    }
+    // generic-proxy accesses to this slot are done; order them before the next bulk copy into it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0 && it + STAGES < my) issue(it + STAGES);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Round-1 TMA kernel (option kernel=1, A/B baseline): persistent CTAs walk CTA tiles (consecutive rows
+// holding <= TILE nonzeros and <= NT rows); one elected thread issues three 1-D bulk copies per tile
+// (values, column indices, row pointers) into a STAGES-deep ring; multiply into shared memory, CTA
+// barrier, one thread per row sums in stored column order, CTA barrier.
 template <int TILE, int MAXROWS>
 struct TmaStage {
   double val[TILE + 8];
@@ -306,10 +504,8 @@ struct TmaStage {
   int rp[MAXROWS + 8];
 };
 
-template <int NT, int TILE, int STAGES, int MODE, int MINB>   // MODE 0: serial row sums, 1: row-mapped multiply, 2: g-lane row sums
-__global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
-  constexpr bool ROWMAP = MODE == 1;
-  constexpr bool GRED = MODE == 2;
+template <int NT, int TILE, int STAGES>
+__global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef TmaStage<TILE, NT> Stage;
   Stage *stages = reinterpret_cast<Stage *>(smem_raw);
@@ -329,9 +525,6 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
   __syncthreads();
 
   const uint64_t pol = l2_policy_evict_first();
-  // producer (thread 0): issue the bulk copies of local tile j into ring slot j % STAGES
-  // (the descriptor of the NEXT tile is fetched one issue ahead so the elected thread never
-  // stalls on a global load between a tile's barrier and the next bulk copy)
   TileDesc dnext = {0, 0, 0, 0};
   if (tid == 0 && my_tiles > 0) dnext = tiles[first];
   auto issue = [&](int j) {
@@ -357,345 +550,19 @@ __global__ void __launch_bounds__(NT, MINB) spmv_tma_kernel(const SpmvOp op) {
   if (tid == 0) {
     for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);   // matrix data only: legal before pdl_wait
   }
-  pdl_wait();   // from here on the vectors written by the previous kernels are read
-  if (tid == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);   // peers' pushes (the local tiles are already in flight)
-  __syncthreads();
-
-  for (int it = 0; it < my_tiles; ++it) {
-    const int slot = it % STAGES;
-    const TileDesc d = sdesc[slot];
-    // when to issue the bulk copies of tile it+STAGES-1 (its slot was freed by the barrier ending
-    // iteration it-1): normally right after this tile's gathers have been queued
-    const bool late_issue = !ROWMAP && d.n <= TILE;
-    if (!late_issue && tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
-    Stage &S = stages[slot];
-    if (d.n <= TILE) {
-      // operands of my row's epilogue: in flight while the tile lands and is multiplied
-      int g = 1;
-      if (ROWMAP || GRED) {
-        while (g < 32 && d.nrows * (g << 1) <= NT) g <<= 1;
-      }
-      const bool has_row = (ROWMAP || GRED) ? (tid < d.nrows * g && (tid & (g - 1)) == 0) : (tid < d.nrows);
-      EpiPre pre;
-      if (has_row) pre = epi_prefetch(op, d.r0 + ((ROWMAP || GRED) ? tid / g : tid));
-      mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
-      const int o = d.s & 3;
-      if (ROWMAP) {
-        // g lanes per row (g = largest power of two with nrows * g <= NT, at most 32): lanes of
-        // neighbouring rows gather neighbouring x entries, so a warp's gather touches few lines
-        const bool active = tid < d.nrows * g;
-        const int row = tid / g, lg = tid & (g - 1);
-        int p = 0, q = 0;
-        if (active) {
-          const int ro = d.r0 & 3;
-          p = S.rp[ro + row] - d.s + o;
-          q = S.rp[ro + row + 1] - d.s + o;
-        }
-        const int qs = op.wlast ? q - 1 : q;
-        double sum = 0.0, xw = 0.0;
-        for (int k = p + lg; k < qs; k += g) sum += S.val[k] * gather_x(op, S.col[k]);
-        if (op.wlast && active && lg == ((qs - p) & (g - 1))) xw = S.val[qs] * gather_x(op, S.col[qs]);
-        for (int w = g >> 1; w > 0; w >>= 1) {   // all lanes of the warp take part (inactive ones carry zeros)
-          sum += __shfl_down_sync(0xffffffffu, sum, w, g);
-          if (op.wlast) xw += __shfl_down_sync(0xffffffffu, xw, w, g);
-        }
-        if (active && lg == 0) epi_finish(op, d.r0 + row, sum, xw, pre);
-      } else {
-        constexpr int kIter = TILE / NT;
-        double xr[kIter];
-#pragma unroll
-        for (int k0 = 0; k0 < kIter; ++k0) {
-          const int k = tid + k0 * NT;
-          xr[k0] = 0.0;
-          if (k < d.n) {
-            xr[k0] = gather_x(op, S.col[o + k]);
-          }
-        }
-        // the latency-critical gathers of THIS tile are queued ahead of the next tile's bulk copies
-        if (late_issue && tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
-#pragma unroll
-        for (int k0 = 0; k0 < kIter; ++k0) {
-          const int k = tid + k0 * NT;
-          if (k < d.n) S.val[o + k] = S.val[o + k] * xr[k0];
-        }
-        __syncthreads();
-        if (GRED) {
-          // g lanes per row read the row's products at consecutive addresses (few bank conflicts) and
-          // shuffle-reduce; the lane-0 thread of a group owns the row's epilogue
-          const bool active = tid < d.nrows * g;
-          const int row = tid / g, lg = tid & (g - 1);
-          int p = 0, q = 0;
-          if (active) {
-            const int ro = d.r0 & 3;
-            p = S.rp[ro + row] - d.s + o;
-            q = S.rp[ro + row + 1] - d.s + o;
-          }
-          double xw = 0.0;
-          if (op.wlast && active) { --q; xw = S.val[q]; }
-          double sum = 0.0;
-          for (int k = p + lg; k < q; k += g) sum += S.val[k];
-          for (int w = g >> 1; w > 0; w >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, w, g);
-          if (has_row) epi_finish(op, d.r0 + row, sum, xw, pre);
-        } else if (has_row) {
-          const int ro = d.r0 & 3;
-          int p = S.rp[ro + tid] - d.s + o;
-          int q = S.rp[ro + tid + 1] - d.s + o;
-          double xw = 0.0;
-          if (op.wlast) { --q; xw = S.val[q]; }
-          double sum = 0.0;
-          for (; p < q; ++p) sum += S.val[p];
-          epi_finish(op, d.r0 + tid, sum, xw, pre);
-        }
-      }
-    } else {
-      mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
-      const int e = d.s + d.n;
-      const int last = op.wlast ? e - 1 : e;
-      double part = 0.0;
-      for (int k = d.s + tid; k < last; k += NT) part += ld_stream(op.val + k) * gather_x(op, ld_stream(op.col + k));
-#pragma unroll
-      for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(0xffffffffu, part, w);
-      if ((tid & 31) == 0) red[tid >> 5] = part;
-      __syncthreads();
-      if (tid == 0) {
-        double sum = 0.0;
-        for (int w = 0; w < NT / 32; ++w) sum += red[w];
-        const double xw = op.wlast ? op.val[last] * gather_x(op, op.col[last]) : 0.0;
-        row_epilogue(op, d.r0, sum, xw);
-      }
-    }
-    // generic-proxy accesses to this slot are done; order them before the next bulk copy into it
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Second TMA kernel: NOTHING in a tile's processing waits on global memory.
-//   * matrix stream (values, columns, row pointers): TMA bulk copies, STAGES-deep ring (as above);
-//   * x gathers of tile t+1: issued as 8-byte cp.async (LDGSTS) into a double-buffered shared array
-//     while tile t is being reduced -- the dependent gather latency is off the critical path;
-//   * epilogue operands of tile t+1: register prefetch one tile ahead;
-//   * multiply + reduce fused: g lanes per row (g = largest power of two with rows*g <= NT, <= 32)
-//     read values and gathered x from shared memory, shuffle-reduce, lane 0 runs the epilogue.
-__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int NT, int TILE, int STAGES>
-__global__ void __launch_bounds__(NT) spmv_tma2_kernel(const SpmvOp op) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  typedef TmaStage<TILE, NT> Stage;
-  Stage *stages = reinterpret_cast<Stage *>(smem_raw);
-  double *xring = reinterpret_cast<double *>(smem_raw + sizeof(Stage) * STAGES);   // [2][TILE]
-  __shared__ __align__(8) uint64_t full[STAGES];
-  __shared__ TileDesc sdesc[STAGES];
-  __shared__ double red[NT / 32 + 1];
-  const int tid = threadIdx.x;
-  const TileDesc *__restrict__ tiles = op.tiles;
-  const int ntiles = op.ntiles;
-  const int first = blockIdx.x, stride = gridDim.x;
-  const int my_tiles = (first < ntiles) ? (ntiles - first + stride - 1) / stride : 0;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const uint64_t pol = l2_policy_evict_first();
-  TileDesc dnext = {0, 0, 0, 0};
-  if (tid == 0 && my_tiles > 0) dnext = tiles[first];
-  auto issue = [&](int j) {
-    const TileDesc d = dnext;
-    if (j + 1 < my_tiles) dnext = tiles[first + (j + 1) * stride];
-    const int slot = j % STAGES;
-    sdesc[slot] = d;
-    if (d.n <= TILE) {
-      Stage &S = stages[slot];
-      const int s_al = d.s & ~3;
-      const int cnt = (d.n + (d.s - s_al) + 3) & ~3;
-      const int r_al = d.r0 & ~3;
-      const int rcnt = (d.nrows + 1 + (d.r0 - r_al) + 3) & ~3;
-      mbar_expect_tx(&full[slot], (uint32_t)(cnt * 12 + rcnt * 4));
-      tma_load_1d(S.val, op.val + s_al, (uint32_t)(cnt * 8), &full[slot], pol);
-      tma_load_1d(S.col, op.col + s_al, (uint32_t)(cnt * 4), &full[slot], pol);
-      tma_load_1d(S.rp, op.rp + r_al, (uint32_t)(rcnt * 4), &full[slot], pol);
-    } else {
-      mbar_expect_tx(&full[slot], 0);
-    }
-  };
-  // lanes per row of a tile
-  auto lanes_per_row = [](int nrows) { int g = 1; while (g < 32 && nrows * (g << 1) <= NT) g <<= 1; return g; };
-  // stage the gathers + epilogue operands of local tile j (its matrix data must have landed)
-  EpiPre pre_next;
-  auto stage_gathers = [&](int j) {
-    const int slot = j % STAGES;
-    const TileDesc d = sdesc[slot];
-    mbar_wait(&full[slot], (uint32_t)((j / STAGES) & 1));
-    if (d.n <= TILE) {
-      const Stage &S = stages[slot];
-      double *xs = xring + (j & 1) * TILE;
-      const int o = d.s & 3;
-      constexpr int kIter = TILE / NT;
-#pragma unroll
-      for (int k0 = 0; k0 < kIter; ++k0) {
-        const int k = tid + k0 * NT;
-        if (k < d.n) {
-          const int c = S.col[o + k];
-          const double *src = (op.xg != nullptr && c >= op.nloc) ? op.xg + (c - op.nloc) : op.x + c;
-          cp_async8(xs + k, src);
-        }
-      }
-      const int g = lanes_per_row(d.nrows);
-      if (tid < d.nrows * g && (tid & (g - 1)) == 0) pre_next = epi_prefetch(op, d.r0 + tid / g);
-    }
-    cp_async_commit();
-  };
-  pdl_launch_dependents();
-  if (tid == 0) {
-    for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);
-  }
   pdl_wait();
   if (tid == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
   __syncthreads();
-  if (my_tiles > 0) stage_gathers(0);
-
-  for (int it = 0; it < my_tiles; ++it) {
-    const int slot = it % STAGES;
-    if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);  // slot freed by the barrier ending iteration it-1
-    const TileDesc d = sdesc[slot];
-    Stage &S = stages[slot];
-    const EpiPre pre = pre_next;
-    if (it + 1 < my_tiles) { stage_gathers(it + 1); cp_async_wait<1>(); }   // tile it's gathers are complete, tile it+1's in flight
-    else cp_async_wait<0>();
-    __syncthreads();
-    if (d.n <= TILE) {
-      const double *xs = xring + (it & 1) * TILE;
-      const int o = d.s & 3;
-      const int g = lanes_per_row(d.nrows);
-      const bool active = tid < d.nrows * g;
-      const int row = tid / g, lg = tid & (g - 1);
-      int p = 0, q = 0;
-      if (active) {
-        const int ro = d.r0 & 3;
-        p = S.rp[ro + row] - d.s;      // tile-relative
-        q = S.rp[ro + row + 1] - d.s;
-      }
-      const int qs = op.wlast ? q - 1 : q;
-      double sum = 0.0, xw = 0.0;
-      for (int k = p + lg; k < qs; k += g) sum += S.val[o + k] * xs[k];
-      if (op.wlast && active && lg == ((qs - p) & (g - 1))) xw = S.val[o + qs] * xs[qs];
-      for (int w = g >> 1; w > 0; w >>= 1) {
-        sum += __shfl_down_sync(0xffffffffu, sum, w, g);
-        if (op.wlast) xw += __shfl_down_sync(0xffffffffu, xw, w, g);
-      }
-      if (active && lg == 0) epi_finish(op, d.r0 + row, sum, xw, pre);
-    } else {
-      const int e = d.s + d.n;
-      const int last = op.wlast ? e - 1 : e;
-      double part = 0.0;
-      for (int k = d.s + tid; k < last; k += NT) part += ld_stream(op.val + k) * gather_x(op, ld_stream(op.col + k));
-#pragma unroll
-      for (int w = 16; w > 0; w >>= 1) part += __shfl_xor_sync(0xffffffffu, part, w);
-      if ((tid & 31) == 0) red[tid >> 5] = part;
-      __syncthreads();
-      if (tid == 0) {
-        double sum = 0.0;
-        for (int w = 0; w < NT / 32; ++w) sum += red[w];
-        const double xw = op.wlast ? op.val[last] * gather_x(op, op.col[last]) : 0.0;
-        row_epilogue(op, d.r0, sum, xw);
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Wide-tile TMA kernel for operators with very short rows (levels 1-4 of upwind problems: 1-3 nonzeros
-// per row).  With <= NT rows per tile such a tile moves only ~5 KB while the per-tile latency chain
-// (wait, gather, barrier, reduce, barrier) is ~1.5 us regardless of its size; here a tile holds up to
-// MAXROWS = 4 NT rows, every thread reduces up to 4 rows, and the rows' epilogue operands arrive with the
-// tile as extra bulk copies (contiguous row range) instead of per-thread register prefetches.
-template <int TILE, int MAXROWS, int NOPD>
-struct WideStage {
-  double val[TILE + 8];
-  double opd[NOPD][MAXROWS + 2];
-  int col[TILE + 8];
-  int rp[MAXROWS + 8];
-};
-
-template <int NT, int TILE, int MAXROWS, int STAGES>
-__global__ void __launch_bounds__(NT) spmv_tma_wide_kernel(const SpmvOp op) {
-  constexpr int NOPD = 3;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  typedef WideStage<TILE, MAXROWS, NOPD> Stage;
-  Stage *stages = reinterpret_cast<Stage *>(smem_raw);
-  __shared__ __align__(8) uint64_t full[STAGES];
-  __shared__ TileDesc sdesc[STAGES];
-  __shared__ int sshift[STAGES][NOPD];
-  __shared__ double red[NT / 32 + 1];
-  const int tid = threadIdx.x;
-  const TileDesc *__restrict__ tiles = op.tiles;
-  const int ntiles = op.ntiles;
-  const int first = blockIdx.x, stride = gridDim.x;
-  const int my_tiles = (first < ntiles) ? (ntiles - first + stride - 1) / stride : 0;
-  const int nstg = op.n_stg;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const uint64_t pol = l2_policy_evict_first();
-  TileDesc dnext = {0, 0, 0, 0};
-  if (tid == 0 && my_tiles > 0) dnext = tiles[first];
-  auto issue = [&](int j) {
-    const TileDesc d = dnext;
-    if (j + 1 < my_tiles) dnext = tiles[first + (j + 1) * stride];
-    const int slot = j % STAGES;
-    sdesc[slot] = d;
-    if (d.n <= TILE) {
-      Stage &S = stages[slot];
-      const int s_al = d.s & ~3;
-      const int cnt = (d.n + (d.s - s_al) + 3) & ~3;
-      const int r_al = d.r0 & ~3;
-      const int rcnt = (d.nrows + 1 + (d.r0 - r_al) + 3) & ~3;
-      uint32_t bytes = (uint32_t)(cnt * 12 + rcnt * 4);
-      unsigned long long a_al[NOPD]; uint32_t ob[NOPD];
-      for (int k = 0; k < nstg; ++k) {
-        const unsigned long long a = (unsigned long long)(epi_field_ptr(op, op.stg_field[k]) + d.r0);
-        a_al[k] = a & ~15ull;
-        const int sh = (int)((a - a_al[k]) >> 3);
-        sshift[slot][k] = sh;
-        ob[k] = (uint32_t)(((d.nrows + sh + 1) & ~1) * 8);
-        bytes += ob[k];
-      }
-      mbar_expect_tx(&full[slot], bytes);
-      tma_load_1d(S.val, op.val + s_al, (uint32_t)(cnt * 8), &full[slot], pol);
-      tma_load_1d(S.col, op.col + s_al, (uint32_t)(cnt * 4), &full[slot], pol);
-      tma_load_1d(S.rp, op.rp + r_al, (uint32_t)(rcnt * 4), &full[slot], pol);
-      for (int k = 0; k < nstg; ++k) tma_load_1d(S.opd[k], (const void *)a_al[k], ob[k], &full[slot], pol);
-    } else {
-      mbar_expect_tx(&full[slot], 0);
-    }
-  };
-  pdl_launch_dependents();
-  pdl_wait();   // the staged operands are vectors written by the previous kernels
-  if (tid == 0) {
-    ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
-    for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);
-  }
-  __syncthreads();
 
   for (int it = 0; it < my_tiles; ++it) {
     const int slot = it % STAGES;
     const TileDesc d = sdesc[slot];
     Stage &S = stages[slot];
-    mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
     if (d.n <= TILE) {
+      const bool has_row = tid < d.nrows;
+      EpiPre pre;
+      if (has_row) pre = epi_prefetch(op, d.r0 + tid);
+      mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
       const int o = d.s & 3;
       constexpr int kIter = TILE / NT;
       double xr[kIter];
@@ -705,6 +572,7 @@ __global__ void __launch_bounds__(NT) spmv_tma_wide_kernel(const SpmvOp op) {
         xr[k0] = 0.0;
         if (k < d.n) xr[k0] = gather_x(op, S.col[o + k]);
       }
+      // the latency-critical gathers of THIS tile are queued ahead of the next tile's bulk copies
       if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
 #pragma unroll
       for (int k0 = 0; k0 < kIter; ++k0) {
@@ -712,20 +580,19 @@ __global__ void __launch_bounds__(NT) spmv_tma_wide_kernel(const SpmvOp op) {
         if (k < d.n) S.val[o + k] = S.val[o + k] * xr[k0];
       }
       __syncthreads();
-      const int ro = d.r0 & 3;
-      for (int r = tid; r < d.nrows; r += NT) {
-        int p = S.rp[ro + r] - d.s + o;
-        int q = S.rp[ro + r + 1] - d.s + o;
+      if (has_row) {
+        const int ro = d.r0 & 3;
+        int p = S.rp[ro + tid] - d.s + o;
+        int q = S.rp[ro + tid + 1] - d.s + o;
         double xw = 0.0;
         if (op.wlast) { --q; xw = S.val[q]; }
         double sum = 0.0;
         for (; p < q; ++p) sum += S.val[p];
-        EpiPre pre = epi_prefetch_masked(op, d.r0 + r, op.stg_mask);
-        for (int k = 0; k < nstg; ++k) epi_set_field(pre, op.stg_field[k], S.opd[k][sshift[slot][k] + r]);
-        epi_finish(op, d.r0 + r, sum, xw, pre);
+        epi_finish(op, d.r0 + tid, sum, xw, pre);
       }
     } else {
       if (tid == 0 && it + STAGES - 1 < my_tiles) issue(it + STAGES - 1);
+      mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
       const int e = d.s + d.n;
       const int last = op.wlast ? e - 1 : e;
       double part = 0.0;
@@ -853,24 +720,6 @@ __global__ void ack_kernel(const unsigned long long *peer_flags, const unsigned 
   for (unsigned m = srcmask; m; m &= m - 1) {
     const int q = __ffs(m) - 1;
     st_release_sys(reinterpret_cast<unsigned *>(peer_flags[q]) + flag_ack(max_inst, inst, me), e);
-  }
-}
-
-// Single-CTA "tail": runs a whole list of ops (the small coarse levels: restrictions, coarse
-// solve, prolongation + smoothing) back to back with CTA barriers instead of kernel launches.
-__global__ void __launch_bounds__(kTailThreads) tail_kernel(const DevOp *ops, int nops) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ double prod[kTile];
-  __shared__ double red[kTailThreads / 32];
-  for (int o = 0; o < nops; ++o) {
-    const DevOp &d = ops[o];
-    if (d.kind == 0) {
-      for (int b = 0; b < d.s.nblk; ++b) process_block<kTailThreads>(d.s, b, prod, red);
-    } else {
-      for (int i = threadIdx.x; i < d.e.n; i += kTailThreads) ew_apply(d.e, i);
-    }
-    __syncthreads();
   }
 }
 

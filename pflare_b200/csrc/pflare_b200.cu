@@ -63,14 +63,11 @@ int fail(int code, const char *fmt, ...) {
 // PFLARE_TOL_ZERO: single-precision literal 1e-12 widened to double (src/Pflare_Parameters.F90:206)
 const double kTolZero = (double)1e-12f;
 
-// TMA-pipelined kernel variants: {threads (= max rows per tile), nnz per tile, pipeline stages}
-struct Variant { int nt, tile, stages; };
-const Variant kVariants[] = {{0, 0, 0}, {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {256, 2048, 3}, {512, 2048, 2}, {512, 4096, 2}, {128, 512, 3}, {128, 1024, 4},
-                             {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {512, 2048, 2}, {128, 512, 3},   // 9..13: row-mapped multiply
-                             {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 2}, {256, 1024, 3}, {128, 512, 2}, {128, 512, 3},  // 14..19: register-capped for more resident CTAs
-                             {256, 1024, 3}, {256, 1024, 4}, {256, 2048, 3}, {512, 2048, 3}, {128, 512, 4},  // 20..24: asynchronous gathers (spmv_tma2_kernel)
-                             {256, 1024, 2}, {256, 1024, 3}, {256, 2048, 2}, {512, 2048, 2}};  // 25..28: nnz-mapped multiply + g-lane row sums
-const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+// SpMV kernels (option "kernel"): 0 = first-generation smem-staged stream kernel (also the fallback for
+// operators with rows longer than a warp tile), 1 = round-1 TMA kernel with CTA tiles (A/B baseline),
+// 2 = warp-tile kernel (default).  Geometry of the round-1 kernel's CTA tiles:
+constexpr int kR1Threads = 256, kR1Tile = 1024, kR1Stages = 2;
+constexpr int kWtWarps = 8;   // warps per CTA of the warp-tile kernel
 
 struct HostCSR {
   bool set = false;
@@ -120,8 +117,12 @@ struct DevCSR {
   int ntiles = 0;
   int ntiles_int = 0;      // the first ntiles_int tiles reference no ghost column (interior), the rest do (boundary)
   TileDesc *tiles = nullptr;
+  // warp-tile storage (kernel 2): one blob per tile + descriptor list, interior tiles first
+  unsigned char *blob = nullptr;
+  WtDesc *wdesc = nullptr;
+  int nwt = 0, nwt_int = 0, rq = 1;
+  bool wt = false;         // this operator runs on the warp-tile kernel (no row longer than a tile)
   DevPlan *xp = nullptr;   // ghost exchange (multi-rank)
-  bool wide = false;       // very short rows: tiles of up to 1024 rows for spmv_tma_wide_kernel
   bool is_set = false;
   bool valid() const { return is_set; }
 };
@@ -191,9 +192,7 @@ struct Ctx {
   int maxn = 0;
   // program
   std::vector<Op> prog;
-  int tail_begin = -1, tail_end = -1;  // [begin,end) range of ops executed by the tail kernel
-  DevOp *d_tail = nullptr;
-  int tail_levels = 0;
+  int tail_levels = 0;                  // levels collapsed into the dense tail
   // dense collapsed tail: the sub-cycle of levels >= dense_level as ONE n x n matrix (x_l = T b_l)
   std::vector<Op> dense_prog;           // the ops it replaces (run once per unit vector at setup)
   int dense_level = 0, dense_n = 0;
@@ -205,12 +204,12 @@ struct Ctx {
   int graph_kernels = 0;
   // options
   int use_graph = 1, fuse = 1;
-  int tail_rows = 0;     // levels with <= this many rows run in the single-CTA tail kernel (0 = off: measured slower than graph nodes)
-  int64_t tail_nnz = 40000;
+  int fuse_epi = 1;      // compile-time specialised epilogue classes (0: every op runs the generic epilogue)
   int dense_rows = 4096; // levels with <= this many rows are collapsed into one dense matrix (0 = off)
-  int kernel = 1;        // 0: smem-staged stream kernel, 1..: TMA-pipelined variants (kVariants)
-  int tile_kernel = 1;   // the variant the uploaded tile lists were built for
+  int kernel = 2;        // 0: smem-staged stream kernel, 1: round-1 TMA kernel (CTA tiles), 2: warp-tile kernel
+  int wt_stages = 3;     // ring depth of the warp-tile kernel (3 or 4 tiles per warp)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
+  int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
   int pdl = 1;           // programmatic dependent launch between the kernels of the cycle
   int64_t agg_rows = 262144;  // levels with <= this many GLOBAL rows are agglomerated onto rank 0 (multi-rank)
   int num_sms = 148;
@@ -226,9 +225,6 @@ struct Ctx {
   double *child_b = nullptr, *child_x = nullptr;  // rank 0: global natural vectors of level l_agg
   double ghost_bytes = 0; int xchg_groups = 0;
   // peer-memory ghost exchange (option p2p): one arena per rank = [flag block | ghost buffers], mapped by every peer
-  int wide_min_rows = 32768;
-  double wide_rows = 0.0; // operators with fewer nonzeros per row than this (and >= wide_min_rows rows) use the wide-tile kernel
-                          // (0 = off, the default: measured 15 % slower per cycle than 256-row tiles in round 1)
   int overlap = 1;       // NCCL exchange on a side stream, overlapped with the interior tiles of the SpMV
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -317,15 +313,27 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int s
   }
   if (c->device < 0) return 0;  // host-only planning context
   int rc;
+  d->wt = false;
+  if (c->kernel == 2) {
+    WtHost W;
+    build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), &W);
+    if (W.ok) {
+      d->wt = true; d->rq = W.rq;
+      d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
+      if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
+      if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
+      d->ntiles = d->nwt; d->ntiles_int = d->nwt_int;
+      return 0;
+    }
+  }
+  // CSR stream (kernel 0 / 1, or a row longer than a warp tile)
   if ((rc = dev_upload_padded(c, &d->rp, h.ia, 8))) return rc;
   if ((rc = dev_upload_padded(c, &d->col, h.ja, 8))) return rc;
   if ((rc = dev_upload_padded(c, &d->val, h.a, 8))) return rc;
   std::vector<int> blk = make_blocks(h.ia, h.m);
   d->nblk = (int)blk.size() - 1;
   if ((rc = dev_upload(c, &d->blk, blk))) return rc;
-  const Variant &V = kVariants[c->tile_kernel];
-  d->wide = c->kernel != 0 && c->wide_rows > 0 && h.m >= c->wide_min_rows && (double)h.nnz() < c->wide_rows * (double)h.m;
-  std::vector<int> tb = d->wide ? make_blocks(h.ia, h.m, 1024, 1024) : make_blocks(h.ia, h.m, V.tile, V.nt);
+  std::vector<int> tb = make_blocks(h.ia, h.m, kR1Tile, kR1Threads);
   std::vector<TileDesc> tiles(tb.size() - 1);
   for (size_t t = 0; t + 1 < tb.size(); ++t) tiles[t] = TileDesc{tb[t], tb[t + 1] - tb[t], h.ia[tb[t]], h.ia[tb[t + 1]] - h.ia[tb[t]]};
   d->ntiles = (int)tiles.size();
@@ -426,10 +434,26 @@ struct Builder {
     SpmvOp s{};
     s.rp = A.rp; s.col = A.col; s.val = A.val; s.m = A.m; s.nblk = A.nblk; s.blk = A.blk;
     s.tiles = A.tiles; s.ntiles = A.ntiles;
+    s.blob = A.blob; s.wdesc = A.wdesc; s.nwt = A.wt ? A.nwt : 0; s.rq = A.rq;
     s.x = x; s.nloc = A.n; s.beta = 1.0;
     s.xg = A.xp ? A.xp->d_xg : nullptr;
-    s.wide = A.wide ? 1 : 0;
     return s;
+  }
+  // epilogue class of an op (kernels.cuh: the compile-time specialisations of the warp-tile kernel)
+  static int classify(const SpmvOp &s) {
+    if (s.D || s.neumann || s.out2) return EPI_GENERIC;
+    if (s.wlast) {
+      if (!s.aux || !s.wout || s.acc_mode) return EPI_GENERIC;
+      if (s.fd_its > 0) return s.out_mode == 0 ? EPI_AFCW_LOCAL : EPI_GENERIC;
+      return (s.out_mode == 1 && !s.wout_idx) ? EPI_AFCW : EPI_GENERIC;
+    }
+    if (s.wout || s.wout_idx) return EPI_GENERIC;
+    if (s.acc_mode) return (s.aux && !s.aux_idx && s.out_mode == 1) ? EPI_AXPBY_ACC : EPI_GENERIC;
+    if (!s.aux) {
+      if (s.beta != 1.0) return EPI_GENERIC;
+      return s.out_mode == 2 ? EPI_ADD : (s.out_mode == 1 ? EPI_SET : EPI_GENERIC);
+    }
+    return s.out_mode == 1 ? EPI_AXPBY : EPI_GENERIC;
   }
   void push_spmv(const SpmvOp &s, const DevCSR &A, int tag, int aux_reads, int w, double extra_bytes = 0) {
     const bool xchg = A.xp && A.xp->global_any;
@@ -450,24 +474,18 @@ struct Builder {
     }
     Op o;
     o.kind = OPK_SPMV; o.s = s; o.level = level; o.tag = tag;
+    o.s.epi = c->fuse_epi ? classify(s) : EPI_GENERIC;
     o.bytes = spmv_bytes(A, aux_reads, w) + extra_bytes;
     o.nnz = (double)(A.nnz_model >= 0 ? A.nnz_model : A.nnz);
-    if (A.wide) {
-      // which epilogue operands travel with the tile (at most 3, in this priority); the rest are loaded per row
-      const bool need[9] = {false, s.aux != nullptr, s.D != nullptr, s.neumann != 0, s.fd_its > 0, s.fd_its > 0, s.out_mode == 2,
-                            s.acc_mode != 0 && s.acc_src != nullptr, s.acc_mode == 2};
-      const int order[8] = {1, 6, 4, 5, 2, 3, 7, 8};
-      o.s.n_stg = 0; o.s.stg_mask = 0;
-      for (int f : order)
-        if (need[f] && o.s.n_stg < 3) { o.s.stg_field[o.s.n_stg++] = (unsigned char)f; o.s.stg_mask |= 1u << (f - 1); }
-    }
-    if (xchg && !p2p && use_p2p && c->overlap && c->kernel != 0) {
+    if (xchg && !p2p && use_p2p && c->overlap && (A.wt || c->kernel == 1)) {
       // split-phase MatMult_MPIAIJ: exchange on the side stream || interior tiles; then the boundary tiles
       out->back().async = true;
       const double fi = A.ntiles > 0 ? (double)A.ntiles_int / A.ntiles : 1.0;
       Op oi = o, ob = o;
       oi.s.ntiles = A.ntiles_int; oi.bytes = o.bytes * fi; oi.nnz = o.nnz * fi;
-      ob.s.tiles = A.tiles + A.ntiles_int; ob.s.ntiles = A.ntiles - A.ntiles_int; ob.bytes = o.bytes - oi.bytes; ob.nnz = o.nnz - oi.nnz;
+      ob.s.ntiles = A.ntiles - A.ntiles_int; ob.bytes = o.bytes - oi.bytes; ob.nnz = o.nnz - oi.nnz;
+      if (A.wt) { oi.s.nwt = A.nwt_int; ob.s.wdesc = A.wdesc + A.nwt_int; ob.s.nwt = A.nwt - A.nwt_int; }
+      else ob.s.tiles = A.tiles + A.ntiles_int;
       Op wt; wt.kind = OPK_XWAIT; wt.level = level; wt.tag = 10;
       out->push_back(oi); out->push_back(wt); out->push_back(ob);
       return;
@@ -802,57 +820,72 @@ cudaError_t launch_k(bool pdl, K kern, int grid, int block, size_t smem, cudaStr
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
-template <int NT, int TILE, int STAGES, int MODE = 0, int MINB = 1>
-int launch_tma(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_tma_kernel<NT, TILE, STAGES, MODE, MINB>;
-  const size_t smem = sizeof(TmaStage<TILE, NT>) * STAGES;
-  static int per_sm = 0;   // resident CTAs per SM of this instantiation (occupancy calculator, once)
-  if (per_sm == 0) {
+// resident CTAs per SM of one kernel instantiation (attribute + occupancy calculator, once per process)
+template <class K>
+int kernel_per_sm(K kern, int threads, size_t smem, int *per_sm) {
+  if (*per_sm == 0) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem));
-    per_sm = std::max(nb, 1);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
+    *per_sm = std::max(nb, 1);
   }
-  if (dry) return 0;
-  const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
-  const int grid = std::min(s.ntiles, c->num_sms * want);   // persistent: a multiple of the SM count
-  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, NT, smem, st, s));
   return 0;
 }
 
-template <int NT, int TILE, int STAGES>
-int launch_tma2(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_tma2_kernel<NT, TILE, STAGES>;
-  const size_t smem = sizeof(TmaStage<TILE, NT>) * STAGES + 2 * TILE * sizeof(double);
+int launch_r1(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  auto kern = spmv_tma_kernel<kR1Threads, kR1Tile, kR1Stages>;
+  const size_t smem = sizeof(TmaStage<kR1Tile, kR1Threads>) * kR1Stages;
   static int per_sm = 0;
-  if (per_sm == 0) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem));
-    per_sm = std::max(nb, 1);
-  }
-  if (dry) return 0;
+  int rc = kernel_per_sm(kern, kR1Threads, smem, &per_sm);
+  if (rc || dry) return rc;
   const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
-  const int grid = std::min(s.ntiles, c->num_sms * want);
-  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, NT, smem, st, s));
+  int grid = std::min(s.ntiles, c->num_sms * want);   // persistent: a multiple of the SM count
+  if (c->max_ctas > 0) grid = std::min(grid, c->max_ctas);
+  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, kR1Threads, smem, st, s));
   return 0;
 }
 
-template <int NT, int TILE, int MAXROWS, int STAGES>
-int launch_wide(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_tma_wide_kernel<NT, TILE, MAXROWS, STAGES>;
-  const size_t smem = sizeof(WideStage<TILE, MAXROWS, 3>) * STAGES;
+// warp-tile kernel: one instantiation per (epilogue class, rows per lane, ghost columns, ring depth)
+template <int EPI, int RQ, bool GH, int ST>
+int launch_wt_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  auto kern = spmv_wt_kernel<EPI, RQ, GH, kWtWarps, ST>;
+  const size_t smem = (size_t)kWtWarps * (ST * kWtStageBytes + (EpiT<EPI>::kXw ? RQ * 32 * 8 : 0));
   static int per_sm = 0;
-  if (per_sm == 0) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem));
-    per_sm = std::max(nb, 1);
-  }
-  if (dry) return 0;
-  const int grid = std::min(s.ntiles, c->num_sms * per_sm);
-  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, NT, smem, st, s));
+  int rc = kernel_per_sm(kern, kWtWarps * 32, smem, &per_sm);
+  if (rc || dry) return rc;
+  const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
+  int grid = std::min((s.nwt + kWtWarps - 1) / kWtWarps, c->num_sms * want);   // persistent
+  if (c->max_ctas > 0) grid = std::min(grid, c->max_ctas);
+  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, kWtWarps * 32, smem, st, s));
   return 0;
+}
+template <int EPI, int RQ>
+int launch_wt_rq(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  const bool gh = s.xg != nullptr;
+  if (c->wt_stages == 4) return gh ? launch_wt_inst<EPI, RQ, true, 4>(c, s, st, dry) : launch_wt_inst<EPI, RQ, false, 4>(c, s, st, dry);
+  return gh ? launch_wt_inst<EPI, RQ, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, RQ, false, 3>(c, s, st, dry);
+}
+template <int EPI>
+int launch_wt_epi(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  switch (s.rq) {
+    case 1: return launch_wt_rq<EPI, 1>(c, s, st, dry);
+    case 2: return launch_wt_rq<EPI, 2>(c, s, st, dry);
+    case 4: return launch_wt_rq<EPI, 4>(c, s, st, dry);
+    case 8: return launch_wt_rq<EPI, 8>(c, s, st, dry);
+  }
+  return fail(7, "internal: rows-per-lane %d", s.rq);
+}
+int launch_wt(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  switch (s.epi) {
+    case EPI_GENERIC: return launch_wt_epi<EPI_GENERIC>(c, s, st, dry);
+    case EPI_ADD: return launch_wt_epi<EPI_ADD>(c, s, st, dry);
+    case EPI_SET: return launch_wt_epi<EPI_SET>(c, s, st, dry);
+    case EPI_AXPBY: return launch_wt_epi<EPI_AXPBY>(c, s, st, dry);
+    case EPI_AFCW: return launch_wt_epi<EPI_AFCW>(c, s, st, dry);
+    case EPI_AFCW_LOCAL: return launch_wt_epi<EPI_AFCW_LOCAL>(c, s, st, dry);
+    case EPI_AXPBY_ACC: return launch_wt_epi<EPI_AXPBY_ACC>(c, s, st, dry);
+  }
+  return fail(7, "internal: epilogue class %d", s.epi);
 }
 
 __global__ void __launch_bounds__(kThreads) pack_kernel(int n, const int *__restrict__ idx, const double *__restrict__ x, double *__restrict__ out) {
@@ -868,55 +901,21 @@ int launch_pack(Ctx *c, const Op &o, cudaStream_t st) {
   return 0;
 }
 
+// dry = true: only set the kernel attributes / occupancy of the instantiation this op needs (outside any capture)
 int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
   if (o.kind == OPK_SPMV) {
-    if (!dry && (o.s.m == 0 || o.s.ntiles == 0)) return 0;
+    if (o.s.m == 0 || o.s.ntiles == 0) return 0;
     int rc = 0;
-    const int k = c->kernel;
-    if (k != 0 && (o.s.wide || dry)) {
-      rc = launch_wide<256, 1024, 1024, 2>(c, o.s, st, dry);
-      if (rc) return rc;
-      if (!dry) { CUDA_TRY(cudaGetLastError()); return 0; }
+    if (o.s.blob) {
+      rc = launch_wt(c, o.s, st, dry);
+    } else if (c->kernel == 1 && o.s.tiles) {
+      rc = launch_r1(c, o.s, st, dry);
+    } else {
+      if (dry) return 0;
+      int grid = std::min(o.s.nblk, c->num_sms * 8 * 4);
+      CUDA_TRY(launch_k(c->pdl != 0, spmv_stream_kernel, grid, kThreads, 0, st, o.s));
     }
-    switch (k) {
-      case 0: {
-        if (dry) return 0;
-        int grid = std::min(o.s.nblk, c->num_sms * 8 * 4);
-        CUDA_TRY(launch_k(c->pdl != 0, spmv_stream_kernel, grid, kThreads, 0, st, o.s));
-        break;
-      }
-      case 1: rc = launch_tma<256, 1024, 2>(c, o.s, st, dry); break;
-      case 2: rc = launch_tma<256, 1024, 3>(c, o.s, st, dry); break;
-      case 3: rc = launch_tma<256, 2048, 2>(c, o.s, st, dry); break;
-      case 4: rc = launch_tma<256, 2048, 3>(c, o.s, st, dry); break;
-      case 5: rc = launch_tma<512, 2048, 2>(c, o.s, st, dry); break;
-      case 6: rc = launch_tma<512, 4096, 2>(c, o.s, st, dry); break;
-      case 7: rc = launch_tma<128, 512, 3>(c, o.s, st, dry); break;
-      case 8: rc = launch_tma<128, 1024, 4>(c, o.s, st, dry); break;
-      case 9: rc = launch_tma<256, 1024, 2, 1>(c, o.s, st, dry); break;
-      case 10: rc = launch_tma<256, 1024, 3, 1>(c, o.s, st, dry); break;
-      case 11: rc = launch_tma<256, 2048, 2, 1>(c, o.s, st, dry); break;
-      case 12: rc = launch_tma<512, 2048, 2, 1>(c, o.s, st, dry); break;
-      case 13: rc = launch_tma<128, 512, 3, 1>(c, o.s, st, dry); break;
-      case 14: rc = launch_tma<256, 1024, 2, 0, 5>(c, o.s, st, dry); break;
-      case 15: rc = launch_tma<256, 1024, 2, 0, 6>(c, o.s, st, dry); break;
-      case 16: rc = launch_tma<256, 1024, 2, 0, 8>(c, o.s, st, dry); break;
-      case 17: rc = launch_tma<256, 1024, 3, 0, 5>(c, o.s, st, dry); break;
-      case 18: rc = launch_tma<128, 512, 2, 0, 16>(c, o.s, st, dry); break;
-      case 19: rc = launch_tma<128, 512, 3, 0, 12>(c, o.s, st, dry); break;
-      case 20: rc = launch_tma2<256, 1024, 3>(c, o.s, st, dry); break;
-      case 21: rc = launch_tma2<256, 1024, 4>(c, o.s, st, dry); break;
-      case 22: rc = launch_tma2<256, 2048, 3>(c, o.s, st, dry); break;
-      case 23: rc = launch_tma2<512, 2048, 3>(c, o.s, st, dry); break;
-      case 24: rc = launch_tma2<128, 512, 4>(c, o.s, st, dry); break;
-      case 25: rc = launch_tma<256, 1024, 2, 2>(c, o.s, st, dry); break;
-      case 26: rc = launch_tma<256, 1024, 3, 2>(c, o.s, st, dry); break;
-      case 27: rc = launch_tma<256, 2048, 2, 2>(c, o.s, st, dry); break;
-      case 28: rc = launch_tma<512, 2048, 2, 2>(c, o.s, st, dry); break;
-      default: return fail(2, "unknown kernel variant %d", k);
-    }
-    if (rc) return rc;
-    if (dry) return 0;
+    if (rc || dry) return rc;
   } else if (o.kind == OPK_EW) {
     if (dry) return 0;
     if (o.e.n == 0) return 0;
@@ -928,9 +927,17 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
     int grid = std::min((n * 32 + kThreads - 1) / kThreads, c->num_sms * 8);
     CUDA_TRY(launch_k(c->pdl != 0, dense_gemv_kernel, grid, kThreads, 0, st, n, (const double *)c->dense_T, (const double *)o.e.a, o.e.out));
   } else {
+    if (dry) return 0;
     return fail(7, "internal: op kind %d cannot be launched directly", o.kind);
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// kernel attributes of every instantiation an op list needs (must not run inside a stream capture)
+int prepare_ops(Ctx *c, const std::vector<Op> &ops) {
+  for (const Op &o : ops)
+    if (o.kind == OPK_SPMV) { int rc = launch_op(c, o, c->stream, true); if (rc) return rc; }
   return 0;
 }
 
@@ -1095,13 +1102,6 @@ int run_program(Ctx *c, cudaStream_t st, int *nkernels) {
   std::vector<Ctx *> R{c};
   std::vector<const std::vector<Op> *> P{&c->prog};
   for (int i = 0; i < n; ++i) {
-    if (i == c->tail_begin && c->tail_end > c->tail_begin) {
-      CUDA_TRY(launch_k(c->pdl != 0, tail_kernel, 1, kTailThreads, 0, st, (const DevOp *)c->d_tail, c->tail_end - c->tail_begin));
-      CUDA_TRY(cudaGetLastError());
-      ++nk;
-      i = c->tail_end - 1;
-      continue;
-    }
     const Op &o = c->prog[i];
     if (op_is_empty(o)) continue;
     int rc = exec_ops(R, P, i, i + 1, st);
@@ -1113,11 +1113,6 @@ int run_program(Ctx *c, cudaStream_t st, int *nkernels) {
 }
 
 int build_graph(Ctx *c) {
-  {  // kernel attributes / occupancy of the selected SpMV variant, outside the capture
-    Op dummy;
-    int rc0 = launch_op(c, dummy, c->stream, true);
-    if (rc0) return rc0;
-  }
   if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
   if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
   CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -1133,7 +1128,6 @@ int build_graph(Ctx *c) {
 
 int build_program(Ctx *c) {
   c->prog.clear();
-  c->tail_begin = c->tail_end = -1;
   c->tail_levels = 0;
   const int NL = c->no_levels;
   if (NL < 2) return 0;
@@ -1144,29 +1138,17 @@ int build_program(Ctx *c) {
   c->n_inst = 0;
   for (DevPlan &D : c->plans) D.first_inst = D.last_inst = -1;
   if (c->p2p_ready) { Op e; e.kind = OPK_EPOCH; e.tag = 10; c->prog.push_back(e); }
-  // which levels go to the single-CTA tail: the longest suffix of small levels (serial contexts only)
-  int ltail = NL + 1;
-  if (c->nranks == 1) {
-    for (int l = NL; l >= 1; --l) {
-      Level &Lv = c->L[l];
-      int64_t mx = 0;
-      for (const DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.inv_ff.d, &Lv.inv_cc.d}) mx = std::max(mx, A->nnz);
-      if (Lv.n <= c->tail_rows && mx <= c->tail_nnz) ltail = l; else break;
-    }
-  }
-  c->tail_levels = (ltail <= NL) ? NL - ltail + 1 : 0;
   // dense collapsed tail (serial contexts): the longest suffix of levels with <= dense_rows rows
   int ldense = NL + 1, dense_begin = -1, dense_end = -1;
   if (c->nranks == 1 && c->dense_rows > 0 && c->device >= 0) {
     for (int l = NL; l >= 1; --l) { if (c->L[l].n <= c->dense_rows) ldense = l; else break; }
-    if (ldense > ltail || ldense > NL - 1) ldense = NL + 1;   // must contain the single-CTA tail and >= 2 levels
+    if (ldense > NL - 1) ldense = NL + 1;   // >= 2 levels
   }
   // down: b_{l+1} = b_c + Z b_f  (MatRestrict with R = [Z I])
   for (int l = 1; l <= LB - 1; ++l) {
     Level &Lv = c->L[l];
     B.level = l;
     if (l == ldense) dense_begin = (int)c->prog.size();
-    if (l == ltail) c->tail_begin = (int)c->prog.size();
     if (Lv.any_c) B.push_ew(Lv.nc, c->bb + Lv.off + Lv.nf, nullptr, nullptr, 1.0, Lv.bc_save, 1);
     SpmvOp s = B.base(Lv.Z, c->bb + Lv.off);
     s.out = c->bb + Lv.off + Lv.nf; s.out_mode = 2;
@@ -1182,7 +1164,6 @@ int build_program(Ctx *c) {
     // coarse solve: x_L = inv_A_ff(L) b_L  (mg_coarse_shell_apply, src/FC_Smooth.F90:29-49)
     Level &Lv = c->L[NL];
     B.level = NL;
-    if (NL == ltail) c->tail_begin = (int)c->prog.size();
     int rc = B.emit_inv(Lv.inv_ff, Lv.Coarse, Lv.coarse_diag, Lv.n, c->bb + Lv.off, c->xb + Lv.off, 1);
     if (rc) return rc;
   }
@@ -1192,7 +1173,6 @@ int build_program(Ctx *c) {
     B.level = l;
     int rc = B.emit_fc_richardson(Lv, true);
     if (rc) return rc;
-    if (l == ltail) c->tail_end = (int)c->prog.size();
     if (l == ldense) dense_end = (int)c->prog.size();
   }
   if (dense_begin >= 0 && dense_end > dense_begin + 1) {
@@ -1208,24 +1188,9 @@ int build_program(Ctx *c) {
     if (c->dense_level != ldense || c->dense_n != Ld.n) c->dense_built = false;
     c->dense_prog.swap(sub);
     c->dense_level = ldense; c->dense_n = Ld.n;
-    c->tail_begin = c->tail_end = -1;   // superseded
     c->tail_levels = NL - ldense + 1;
   } else {
     c->dense_prog.clear(); c->dense_level = 0; c->dense_n = 0;
-  }
-  if (ltail == NL && c->tail_begin >= 0) c->tail_end = c->tail_begin;  // coarse level alone: not worth a tail
-  if (c->device >= 0 && c->tail_begin >= 0 && c->tail_end > c->tail_begin) {
-    std::vector<DevOp> ops;
-    for (int i = c->tail_begin; i < c->tail_end; ++i) {
-      DevOp d{};
-      d.kind = c->prog[i].kind; d.s = c->prog[i].s; d.e = c->prog[i].e;
-      ops.push_back(d);
-    }
-    int rc = dev_upload(c, &c->d_tail, ops);
-    if (rc) return rc;
-  } else {
-    c->tail_begin = c->tail_end = -1;
-    c->tail_levels = 0;
   }
   if (c->p2p_ready) {
     if (c->n_inst > kMaxInst) return fail(25, "the cycle needs %d ghost exchanges, the flag block holds %d: set option p2p=0", c->n_inst, kMaxInst);
@@ -1237,6 +1202,11 @@ int build_program(Ctx *c) {
   for (const Op &o : c->prog)
     if (o.kind == OPK_XCHG) { c->ghost_bytes += 8.0 * o.xp->plan.n_send(); ++c->xchg_groups; }
     else if (o.kind == OPK_GATHER0 || o.kind == OPK_SCATTER0) { c->ghost_bytes += o.bytes; ++c->xchg_groups; }
+  if (c->device >= 0) {
+    int rc;
+    if ((rc = prepare_ops(c, c->prog))) return rc;
+    if ((rc = prepare_ops(c, c->dense_prog))) return rc;
+  }
   return 0;
 }
 
@@ -1250,7 +1220,6 @@ int build_dense_tail(Ctx *c) {
     if ((rc = dev_alloc(c, &c->dense_T, (size_t)n * n))) return rc;
     c->dense_cap = (size_t)n * n;
   }
-  { Op dummy; if ((rc = launch_op(c, dummy, c->stream, true))) return rc; }
   std::vector<Ctx *> R{c};
   std::vector<const std::vector<Op> *> P{&c->dense_prog};
   const int grid = std::min((n + kThreads - 1) / kThreads, c->num_sms * 8);
@@ -1332,8 +1301,8 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->rank = 0; ch->nranks = 1; ch->device = c->device; ch->no_levels = NL - LA + 1;
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
-  ch->use_graph = 0; ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
-  ch->kernel = c->kernel; ch->tile_kernel = c->tile_kernel; ch->ctas_per_sm = c->ctas_per_sm; ch->wide_rows = c->wide_rows; ch->wide_min_rows = c->wide_min_rows;
+  ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
+  ch->kernel = c->kernel; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
   for (int l = LA; l <= NL; ++l) {
@@ -1482,12 +1451,47 @@ int setup_p2p(Ctx *c) {
   return 0;
 }
 
+void destroy_ctx(Ctx *c);
+
+// Everything a previous finalize_setup built on the device (operators, vectors, plans, dense tail, graph, the
+// child hierarchy of the agglomerated levels) is released, so that set_* + finalize_setup on a live handle
+// (the reference's re-setup, src/PCAIR_Shell.F90:148-162) rebuilds from the new host operators and never
+// mixes old and new state.
+void release_device_state(Ctx *c) {
+  if (c->device >= 0) {
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+    if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+    for (size_t p = 0; p < c->peer_arena.size(); ++p)
+      if (c->peer_ipc[p] && c->peer_arena[p]) cudaIpcCloseMemHandle(c->peer_arena[p]);
+    for (void *p : c->allocs) cudaFree(p);
+  }
+  if (c->child) destroy_ctx(c->child.release());
+  c->peer_arena.clear(); c->peer_ipc.clear();
+  c->allocs.clear(); c->dev_bytes = 0;
+  c->plans.clear(); c->prog.clear(); c->dense_prog.clear();
+  c->dense_T = nullptr; c->dense_cap = 0; c->dense_built = false; c->dense_level = 0; c->dense_n = 0;
+  c->xb = c->bb = c->io_b = c->io_x = nullptr;
+  for (double *&p : c->scr) p = nullptr;
+  c->child_b = c->child_x = nullptr;
+  c->arena = nullptr; c->arena_bytes = 0; c->p2p_ready = false; c->d_peer_flags = nullptr; c->d_done = nullptr;
+  for (Level &Lv : c->L) {
+    for (DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.inv_ff.d, &Lv.inv_cc.d}) *A = DevCSR();
+    Lv.inv_ff.ddiag = Lv.inv_cc.ddiag = nullptr;
+    Lv.aff_diag = Lv.acc_diag = Lv.coarse_diag = Lv.bc_save = nullptr;
+    Lv.d_pos = Lv.d_inv = nullptr;
+  }
+  c->finalized = c->planned = false;
+}
+
 // ------------------------------------------------------------------ setup: the layout
 int finalize_ctx(Ctx *c) {
   const int NL = c->no_levels, P = c->nranks;
   int rc;
   for (int l = 1; l <= NL; ++l)
     if (!c->L[l].set) return fail(2, "level %d was never set", l);
+  if (c->planned || c->finalized || !c->allocs.empty()) release_device_state(c);
   c->plans.clear();
   // sizes must chain locally: n_{l+1} == n_coarse(l)
   for (int l = 1; l < NL; ++l)
@@ -2209,10 +2213,8 @@ static void collect_stats(Ctx *c, double *v) {
     v[1] += o.kind == OPK_XCHG || o.kind == OPK_GATHER0 || o.kind == OPK_SCATTER0 ? 0.0 : o.bytes;
     v[2] += o.nnz;
     if (o.kind == OPK_SPMV || o.kind == OPK_EW) v[5] = std::max(v[5], o.bytes);
-    const bool in_tail = (int)i >= c->tail_begin && (int)i < c->tail_end;
-    if (!in_tail && !op_is_empty(o) && o.kind != OPK_CHILD) ++nk;
+    if (!op_is_empty(o) && o.kind != OPK_CHILD) ++nk;
   }
-  if (c->tail_end > c->tail_begin) ++nk;
   v[0] += nk;
   v[3] += c->dev_bytes;
   v[4] += c->ghost_bytes;
@@ -2270,8 +2272,11 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
 static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   if (k == "graph") c->use_graph = value != 0;
   else if (k == "fuse") c->fuse = value != 0;
-  else if (k == "tail_rows") c->tail_rows = (int)value;
-  else if (k == "tail_nnz") c->tail_nnz = (int64_t)value;
+  else if (k == "epi_classes") c->fuse_epi = value != 0;
+  else if (k == "wt_stages") {
+    if (value != 3 && value != 4) return fail(2, "wt_stages must be 3 or 4");
+    c->wt_stages = (int)value;
+  }
   else if (k == "dense_rows") {
     if (value > 16384) return fail(2, "dense_rows is limited to 16384 (the collapsed tail is a dense n x n fp64 matrix)");
     c->dense_rows = (int)value;
@@ -2282,22 +2287,14 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   }
   else if (k == "kernel") {
     const int v = (int)value;
-    if (v < 0 || v >= kNumVariants) return fail(2, "kernel variant must be 0..%d", kNumVariants - 1);
-    if (c->finalized && v != 0 && v != c->tile_kernel) return fail(2, "kernel variant %d needs other tile lists: set it before finalize_setup", v);
+    if (v < 0 || v > 2) return fail(2, "kernel must be 0 (stream), 1 (round-1 TMA, CTA tiles) or 2 (warp tiles)");
+    if ((c->finalized || c->planned) && v != c->kernel) return fail(2, "the kernel decides the operator storage: set it before finalize_setup");
     c->kernel = v;
-    if (!c->finalized && v != 0) c->tile_kernel = v;
   }
   else if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
+  else if (k == "max_ctas") c->max_ctas = (int)value;
   else if (k == "pdl") c->pdl = value != 0;
   else if (k == "overlap") c->overlap = value != 0;
-  else if (k == "wide_min_rows") {
-    if (c->finalized || c->planned) return fail(2, "wide_min_rows must be set before finalize_setup");
-    c->wide_min_rows = (int)value;
-  }
-  else if (k == "wide_rows") {
-    if (c->finalized || c->planned) return fail(2, "wide_rows must be set before finalize_setup");
-    c->wide_rows = value;
-  }
   else if (k == "p2p") {
     if (c->finalized || c->planned) return fail(2, "p2p must be set before finalize_setup");
     c->p2p = value != 0;
@@ -2305,7 +2302,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
     Ctx *ch = c->child.get();
-    ch->fuse = c->fuse; ch->tail_rows = c->tail_rows; ch->tail_nnz = c->tail_nnz; ch->kernel = c->kernel; ch->ctas_per_sm = c->ctas_per_sm;
+    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
     ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   }
   return 0;
@@ -2331,7 +2328,9 @@ int pflare_b200_set_option(void *handle, const char *key, double value) {
   return rebuild_after_option(c);
 }
 
-static void destroy_ctx(Ctx *c) {
+}  // extern "C"
+namespace {
+void destroy_ctx(Ctx *c) {
   if (c->device >= 0) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
@@ -2347,6 +2346,8 @@ static void destroy_ctx(Ctx *c) {
   c->comm.reset();
   delete c;
 }
+}  // namespace
+extern "C" {
 
 int pflare_b200_destroy(void **handle) {
   if (!handle || !*handle) return 0;
@@ -2422,7 +2423,6 @@ int pflare_b200_cluster_finalize(void *cluster) {
   cl->finalized = true;
   if (cl->device >= 0 && cl->ranks[0]->use_graph && cl->ranks[0]->no_levels >= 2) {
     Ctx *c0 = cl->ranks[0].get();
-    { Op dummy; int rc0 = launch_op(c0, dummy, cl->stream, true); if (rc0) return rc0; }
     if (cl->gexec) { cudaGraphExecDestroy(cl->gexec); cl->gexec = nullptr; }
     if (cl->graph) { cudaGraphDestroy(cl->graph); cl->graph = nullptr; }
     CUDA_TRY(cudaStreamBeginCapture(cl->stream, cudaStreamCaptureModeThreadLocal));

@@ -151,3 +151,14 @@ def test_c_abi_from_plain_c(built_libs, tmp_path):
                            "-Wl,-rpath," + libdir])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "CAPI_HOST_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_warp_tile_format_and_row_sum_algorithm(tmp_path):
+    """The operator storage of spmv_wt_kernel (pflare_b200/csrc/wt_format.h) and the kernel's row-sum algorithm
+    (lane-local walk + segmented warp scan), emulated lane by lane on the CPU against a plain CSR product:
+    random row lengths 1..256, empty rows, the merged A_fc|W (last entry = W) mode, ghost columns."""
+    import subprocess
+    exe = str(tmp_path / "wt_format_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-o", exe, os.path.join(ROOT, "tests", "c", "wt_format_check.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "WT_FORMAT_OK" in out.stdout, out.stdout + out.stderr

@@ -50,25 +50,17 @@ def test_vcycle_parity(built_libs, name, dense_rows):
 
 
 @pytest.mark.parametrize("opts", [dict(graph=0), dict(dense_rows=0), dict(fuse=0, dense_rows=0), dict(pdl=0), dict(pdl=0, dense_rows=0),
-                                  dict(dense_rows=0, tail_rows=2048), dict(dense_rows=0, tail_rows=100000, tail_nnz=1e9),
                                   dict(graph=0, fuse=0, dense_rows=0),
-                                  # SpMV kernel variants: 0 = smem-staged stream kernel, 1.. = TMA-pipelined (stages / tile sizes)
+                                  # SpMV kernels: 0 = smem-staged CSR stream kernel, 1 = round-1 TMA kernel (CTA tiles), 2 = warp tiles (default)
                                   dict(kernel=0, dense_rows=0), dict(kernel=1, dense_rows=0), dict(kernel=2, dense_rows=0),
-                                  dict(kernel=3, dense_rows=0), dict(kernel=4, dense_rows=0), dict(kernel=5, dense_rows=0),
-                                  dict(kernel=6, dense_rows=0), dict(kernel=7, dense_rows=0), dict(kernel=8, dense_rows=0),
-                                  dict(kernel=9, dense_rows=0), dict(kernel=10, dense_rows=0), dict(kernel=11, dense_rows=0),
-                                  dict(kernel=12, dense_rows=0), dict(kernel=13, dense_rows=0),
-                                  # 20..24: spmv_tma2_kernel (asynchronous cp.async gathers, fused multiply/reduce)
-                                  dict(kernel=20, dense_rows=0), dict(kernel=21, dense_rows=0), dict(kernel=22, dense_rows=0),
-                                  dict(kernel=23, dense_rows=0), dict(kernel=24, dense_rows=0),
-                                  # 25..28: nnz-mapped multiply + g-lane (bank-conflict-light) row sums
-                                  dict(kernel=25, dense_rows=0), dict(kernel=26, dense_rows=0), dict(kernel=27, dense_rows=0), dict(kernel=28, dense_rows=0),
-                                  dict(kernel=2, ctas_per_sm=1),
-                                  # wide-tile kernel (up to 1024 rows per tile, TMA-staged epilogue operands) forced onto every operator
-                                  dict(wide_min_rows=0, wide_rows=1e9, dense_rows=0), dict(wide_min_rows=0, dense_rows=0),
-                                  dict(wide_min_rows=0, wide_rows=1e9, dense_rows=0, graph=0, pdl=0), dict(wide_rows=0, dense_rows=0),
+                                  dict(kernel=1, ctas_per_sm=1),
+                                  # warp-tile kernel: ring depth, generic (run-time branched) epilogue instead of the compiled classes,
+                                  # ONE persistent CTA per SM / in total (many tiles per warp: the mbarrier ring wraps many times)
+                                  dict(wt_stages=4, dense_rows=0), dict(epi_classes=0, dense_rows=0), dict(epi_classes=0, fuse=0, dense_rows=0),
+                                  dict(ctas_per_sm=1, dense_rows=0), dict(max_ctas=1, dense_rows=0), dict(max_ctas=1, wt_stages=4, dense_rows=0, graph=0, pdl=0),
+                                  dict(kernel=1, max_ctas=2, dense_rows=0),
                                   # coarse levels collapsed into one dense operator (built from the same kernels at setup)
-                                  dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, tail_rows=0, graph=0)],
+                                  dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, graph=0)],
                          ids=lambda o: ",".join("%s=%g" % kv for kv in o.items()))
 @pytest.mark.parametrize("name", ["fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "fd2d_diagAff", "dg_mf", "fd2d_idealW",
                                   "fd2d_mf_neumann", "fd2d_mf_newton_noextra_dscale"])
