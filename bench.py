@@ -11,12 +11,17 @@ setup on the host before the timed region) and is uploaded once as device CSR.
   e2e      : the same through the reference-facing call with HOST buffers (pinned): H2D of the rhs,
              V-cycle, D2H of the result inside the timed region.
   roofline : HBM; algorithmic bytes (SURVEY.md section 8d model, computed by the library per op) of the
-             spmv_stream_kernel launches / their summed CUDA-event durations.
+             SpMV launches of one V-cycle / the graph-mode cycle time (the SpMV kernel is all but a
+             handful of launches, so the whole cycle time is charged to it: a conservative figure).
+  parity   : relative L2 difference between the GPU result and the CPU oracle's result on the same
+             seeded rhs, at the benchmarked size and transport (every rank checks its rows); the
+             run FAILS above 1e-12.
   cpu_baseline / --impl reference : the CPU oracle (OpenMP restatement of the reference's PETSc
              path, kind "port": PETSc/gfortran are absent so the reference cannot be built) on the
-             same hierarchy, all host threads.
+             same hierarchy, all host threads (set explicitly: torchrun exports OMP_NUM_THREADS=1).
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -162,19 +167,38 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def time_oracle(H, n, cycles, warm=1):
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def make_oracle(H):
+    """The CPU oracle on this hierarchy, with ALL host threads (torchrun exports OMP_NUM_THREADS=1)."""
     import hiergen
     import oracle
     O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))
-    b = np.random.default_rng(1234).random(n)
+    O.set_threads(host_threads())
+    return O
+
+
+def workload_config(name, A, H):
+    """`config` of the JSON line: identical in the b200 and the reference arm."""
+    return {"workload": name, "rows": int(A.shape[0]), "levels": int(H.no_levels), "nnz_level1": int(A.nnz),
+            "rhs": "seeded uniform(0,1), seed 1234",
+            "l2": "inputs larger than L2 (every V-cycle streams the whole hierarchy, > 126 MB), no flush"}
+
+
+def time_oracle(O, b, cycles, warm=1):
     for _ in range(warm):
         O.apply(b)
     ts = []
     for _ in range(cycles):
         t = time.perf_counter()
-        O.apply(b)
+        x = O.apply(b)
         ts.append(time.perf_counter() - t)
-    return float(np.median(ts)), O.threads()
+    return float(np.median(ts)), x
 
 
 def run_reference(args):
@@ -183,25 +207,22 @@ def run_reference(args):
         return
     A, H, name = build_hierarchy(args)
     n = A.shape[0]
-    # each step = one V-cycle of the CPU path on the full workload (bounded: a cycle is O(1 s))
-    import hiergen
-    import oracle
-    O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))
+    # each step = one V-cycle of the CPU path on the full workload (a cycle is O(0.1-1 s): bounded)
+    O = make_oracle(H)
     b = np.random.default_rng(1234).random(n)
-    steps = max(1, min(args.steps, args.ref_max_steps))
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):
         O.apply(b)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(args.steps):
         O.apply(b)
-    dt = (time.perf_counter() - t0) / steps
+    dt = (time.perf_counter() - t0) / args.steps
     val = n / dt
-    sample = "%d full V-cycles of the CPU oracle on the whole workload (%d rows)" % (steps, n)
+    sample = "%d full V-cycles of the CPU oracle on the whole workload (%d rows)" % (args.steps, n)
     out = {
         "impl": "reference", "metric": "AIRG V-cycle DOF/s", "value": val, "unit": "DOF/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "rows": n, "levels": H.no_levels},
+        "config": workload_config(name, A, H),
         "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": O.threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -309,17 +330,50 @@ def run_gpu(args):
     clocks = clk.summary()
     extra = {}
     for kv in args.compare_opt:
-        k, v = kv.split("=")
-        pc.setOption(k, float(v))
+        for one in kv.split(","):
+            k, v = one.split("=")
+            pc.setOption(k, float(v))
         extra[kv] = timed(lambda: dev.apply_ptr(b.data_ptr(), x.data_ptr(), 1), args.steps, args.warmup)
         log("[bench] with %s: %.4f ms per V-cycle (main run %.4f)" % (kv, extra[kv], ms_dev))
     # end-to-end leg: host (pinned) buffers through the reference-facing call
     ms_e2e = timed(lambda: dev.apply_ptr(b_host.data_ptr(), x_host.data_ptr(), 0), args.steps, args.warmup)
 
-    # parity spot check on the fly (small cost): result is finite and deterministic
+    # device-resident and host-buffer applies must agree bit for bit
     dev.synchronize()
     xs = x.cpu().numpy()
     assert np.all(np.isfinite(xs)) and np.array_equal(xs, x_host.numpy()), "device and host-buffer applies differ"
+
+    # parity against the CPU oracle on the same rhs, at THIS size and over THIS transport: rank 0 runs the
+    # oracle (all host threads), every rank checks its own rows
+    cpu = None
+    parity = None
+    if not args.no_parity:
+        xo_full = torch.empty(n, dtype=torch.float64, device="cuda")
+        if rank == 0:
+            O = make_oracle(H)
+            t_cpu, xo = time_oracle(O, b_full, cycles=args.cpu_cycles if (world == 1 and not args.no_cpu_baseline) else 1,
+                                    warm=1 if world == 1 else 0)
+            xo_full.copy_(torch.from_numpy(xo))
+            if world == 1 and not args.no_cpu_baseline:
+                cpu = {"value": n / t_cpu, "unit": "DOF/s", "cores": O.threads(), "kind": "port",
+                       "sample": "median of %d full V-cycles of the CPU oracle (OpenMP restatement of the PETSc path) on the whole workload" % args.cpu_cycles,
+                       "ms_per_cycle": t_cpu * 1e3}
+            O.close()
+        if world > 1:
+            dist.broadcast(xo_full, src=0)
+        xo_loc = xo_full[lo:lo + n_local]
+        num = torch.sum((x - xo_loc) ** 2)
+        den = torch.sum(xo_loc ** 2)
+        nd = torch.stack([num, den])
+        if world > 1:
+            dist.all_reduce(nd)
+        rel = float(torch.sqrt(nd[0] / nd[1]).item())
+        parity = {"rel_l2": rel, "n": int(n), "tol": 1e-12, "against": "CPU oracle (oracle/air_oracle.c) on the same seeded rhs",
+                  "ranks_checked": world}
+        log("[bench] rank %d parity vs oracle: rel L2 = %.3e" % (rank, rel))
+        if not (rel <= 1e-12):
+            raise SystemExit("bench.py: PARITY FAILURE: relative L2 difference %.3e > 1e-12 against the CPU oracle" % rel)
+        del xo_full
 
     # roofline of the dominant kernel: per-launch CUDA events (graph off for this pass)
     reps = 3
@@ -353,35 +407,38 @@ def run_gpu(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # The SpMV mega-op kernel is all but ~3 launches of the cycle.  Its time inside the timed region = graph-mode
-    # cycle time minus the CUDA-event time of the non-SpMV launches (entry/exit permutation, dense tail GEMV,
-    # diagonal-inverse elementwise ops); bytes = the algorithmic bytes of the SpMV launches.
-    other_ms = (allms - tot_ms) / reps
-    other_by = (allby - tot_by) / reps
+    # The SpMV mega-op kernel is all but a handful of launches of the cycle.  achieved = algorithmic bytes of ALL SpMV
+    # launches of one V-cycle / the graph-mode cycle time (the non-SpMV launches' time is charged to the kernel too).
     spmv_by = tot_by / reps
-    spmv_ms = max(ms_dev - other_ms, 1e-6)
-    achieved = spmv_by / (spmv_ms * 1e-3) / 1e9
+    achieved = spmv_by / (ms_dev * 1e-3) / 1e9
     per_launch = tot_by / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+    kernel_id = {0: "spmv_stream_kernel", 1: "spmv_tma_kernel<256,1024,2>", 2: "spmv_wt_kernel"}[int(dict(kv.split("=") for kv in args.opt).get("kernel", 2))]
     roof = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "kernel": "spmv_tma_kernel<256,1024,2> (TMA-pipelined CSR SpMV mega-op)",
+        "kernel": kernel_id + " (CSR SpMV mega-op, all epilogue classes)",
         "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650",
-        "how": "algorithmic bytes of all SpMV launches of one V-cycle / (graph-mode cycle time - CUDA-event time of the non-SpMV launches)",
+        "how": "algorithmic bytes (SURVEY.md 8d) of all SpMV launches of one V-cycle / graph-mode cycle time (CUDA events on the library stream)",
         "achieved_per_launch_events": per_launch,
         "per_launch_events_note": "same bytes / sum of per-launch CUDA-event durations with the graph off (adds event + launch gaps)",
-        "cycle_achieved": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9,      # this rank's bytes / the cycle time
-        "cycle_frac": st["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9 / peak,
+        "frac_of_8TBs_nominal": achieved / 8000.0,
+        "spmv_share_of_cycle_events": tot_ms / allms if allms > 0 else None,
         "largest_launch": {"bytes": biggest[0], "ms": biggest[1], "level": biggest[2],
                            "GBps": biggest[0] / (biggest[1] * 1e-3) / 1e9 if biggest[1] > 0 else None},
-        "algorithmic_bytes_per_cycle": st["algorithmic_bytes"], "nnz_per_cycle": st["nnz_per_cycle"],
+        "algorithmic_bytes_per_cycle": st["algorithmic_bytes"], "spmv_algorithmic_bytes_per_cycle": spmv_by,
+        "nnz_per_cycle": st["nnz_per_cycle"],
     }
-    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of this same workload
-    # (profiles/r01_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per captured launch)
+    # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of this same workload, valid
+    # only for the kernel source it was taken with (the file is stamped with the kernel name and the sha256 of
+    # kernels.cuh; a mismatch means the capture is stale and is NOT reported)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        roof["traffic"] = tr["mean_dram_bytes_per_launch"]
-        roof["traffic_detail"] = {"launches": len(tr["launches"]), "mean_algorithmic_bytes_per_launch": tr["mean_algorithmic_bytes_per_launch"],
-                                  "dram_over_algorithmic": tr["dram_over_algorithmic"], "source": tr["source"]}
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "pflare_b200", "csrc", "kernels.cuh"), "rb").read()).hexdigest()
+        if tr.get("kernel") == kernel_id and tr.get("kernels_cuh_sha256") == sha:
+            roof["traffic"] = tr["mean_dram_bytes_per_launch"]
+            roof["traffic_detail"] = {"launches": len(tr["launches"]), "mean_algorithmic_bytes_per_launch": tr["mean_algorithmic_bytes_per_launch"],
+                                      "dram_over_algorithmic": tr["dram_over_algorithmic"], "source": tr["source"]}
+        else:
+            roof["traffic_detail"] = {"stale": "profiles/r02_ncu_traffic.json was captured with another kernel source (%s)" % tr.get("kernel")}
     except Exception:
         pass
 
@@ -392,30 +449,22 @@ def run_gpu(args):
     job_bytes, job_launches, job_ghost, job_dev = [float(v) for v in tot.tolist()]
     l_agg, glob_rows = dev.layout() if world > 1 else (H.no_levels + 1, None)
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t_cpu, threads = time_oracle(H, n, cycles=args.cpu_cycles)
-        cpu = {"value": n / t_cpu, "unit": "DOF/s", "cores": threads, "kind": "port",
-               "sample": "median of %d full V-cycles of the CPU oracle (OpenMP restatement of the PETSc path) on the whole workload" % args.cpu_cycles,
-               "ms_per_cycle": t_cpu * 1e3}
-
     if rank == 0:
         out = {
             "metric": "AIRG V-cycle DOF/s", "value": n / (ms_dev * 1e-3),
             "unit": "DOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "rows": n, "levels": H.no_levels, "nnz_level1": int(A.nnz),
-                       "l2": "inputs larger than L2: %.2f GB of operators streamed per cycle (whole job), no flush" % (job_bytes / 1e9),
-                       "device_bytes": job_dev, "rhs": "seeded uniform(0,1), seed 1234",
-                       "partition": "1 GPU" if world == 1 else "%d ranks, contiguous row blocks (PETSc MPIAIJ ownership), ghost exchange = %s, levels >= %d agglomerated on rank 0" % (world, "peer-memory push (CUDA IPC)" if any(o.startswith("p2p=1") for o in args.opt) else "NCCL send/recv", l_agg),
-                       "ghost_bytes_per_cycle": job_ghost, "exchange_groups_per_cycle_rank0": int(st["exchange_groups"]),
-                       "library_options": args.opt},
-            "roofline": roof, "cpu_baseline": cpu,
+            "config": workload_config(name, A, H),
+            "details": {"streamed_GB_per_cycle": job_bytes / 1e9, "device_bytes": job_dev,
+                        "partition": "1 GPU" if world == 1 else "%d ranks, contiguous row blocks (PETSc MPIAIJ ownership), ghost exchange = %s, levels >= %d agglomerated on rank 0" % (world, "peer-memory push (CUDA IPC)" if any(o.startswith("p2p=1") for o in args.opt) else "NCCL send/recv", l_agg),
+                        "ghost_bytes_per_cycle": job_ghost, "exchange_groups_per_cycle_rank0": int(st["exchange_groups"]),
+                        "library_options": args.opt},
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "DOF/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n, "note": "summed over ranks"},
             "gpu_launches": int(job_launches) * args.steps,
             "launches_per_cycle": int(st["kernel_launches"]), "tail_levels": int(st["tail_levels"]),
-            "clocks": clocks,
+            "clocks": clocks, "compare_opt_ms": extra,
         }
         print(json.dumps(out), flush=True)
     pc.destroy()
@@ -432,8 +481,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("PFLARE_BENCH_WORKLOAD", "adv_diff_fd_2d"))
     ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("PFLARE_BENCH_N", "4096")))
     ap.add_argument("--cpu-cycles", type=int, default=20)
-    ap.add_argument("--ref-max-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check (development runs only)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-cache", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (repeatable)")

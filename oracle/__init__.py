@@ -107,6 +107,10 @@ class OracleAIR:
     def threads(self):
         return int(self.L.oracle_omp_threads())
 
+    def set_threads(self, n):
+        self.L.oracle_set_omp_threads(int(n))
+        return self.threads()
+
     def close(self):
         if self.h:
             self.L.oracle_destroy(self.h)

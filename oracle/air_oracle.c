@@ -412,6 +412,15 @@ void oracle_destroy(void *h) {
   free(H);
 }
 
+/* bench.py under torchrun inherits OMP_NUM_THREADS=1: the CPU baseline sets its thread count explicitly */
+void oracle_set_omp_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_omp_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -863,6 +863,7 @@ template <int EPI, int RQ>
 int launch_wt_rq(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   const bool gh = s.xg != nullptr;
   if (c->wt_stages == 4) return gh ? launch_wt_inst<EPI, RQ, true, 4>(c, s, st, dry) : launch_wt_inst<EPI, RQ, false, 4>(c, s, st, dry);
+  if (c->wt_stages == 2) return gh ? launch_wt_inst<EPI, RQ, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, RQ, false, 2>(c, s, st, dry);
   return gh ? launch_wt_inst<EPI, RQ, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, RQ, false, 3>(c, s, st, dry);
 }
 template <int EPI>
@@ -2274,7 +2275,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else if (k == "fuse") c->fuse = value != 0;
   else if (k == "epi_classes") c->fuse_epi = value != 0;
   else if (k == "wt_stages") {
-    if (value != 3 && value != 4) return fail(2, "wt_stages must be 3 or 4");
+    if (value != 2 && value != 3 && value != 4) return fail(2, "wt_stages must be 2, 3 or 4");
     c->wt_stages = (int)value;
   }
   else if (k == "dense_rows") {
