@@ -52,6 +52,9 @@ class AirOptions:
     r_drop: float = 0.01
     a_drop: float = 1e-4
     a_lump: bool = False
+    # -pc_air_full_smoothing_up_and_down (AIR_Data_Type.F90:126-127): one Richardson sweep with an approximate
+    # inverse of the WHOLE level matrix down and up (PCMG multiplicative V-cycle) instead of F/C smoothing on the way up
+    full_smoothing_up_and_down: bool = False
     seed: int = 1
 
     @property
@@ -95,6 +98,7 @@ class Level:
     A_cf: Optional[sp.csr_matrix] = None
     A_cc: Optional[sp.csr_matrix] = None
     inv_A_cc: Optional[Inverse] = None
+    A: Optional[sp.csr_matrix] = None     # coarse_matrix(our_level): only kept with full_smoothing_up_and_down
 
 
 @dataclass
@@ -284,10 +288,19 @@ def build_hierarchy(A, opts: AirOptions = None, verbose=False):
             A_fc_drop = _submatrix(Afd, None, cmap, nc)
         else:
             A_ff_drop, A_cf_drop, A_fc_drop = A_ff, A_cf, A_fc
-        inv_ff, asm = make_inverse(A_ff, inv_type, opts.poly_order, sparsity, opts.matrix_free_polys,
-                                   opts.diag_scale_polys, rng, want_assembled=(opts.strong_r_threshold == 0.0))
-        if opts.strong_r_threshold != 0.0:
-            _, asm = make_inverse(A_ff_drop, inv_type, opts.poly_order, sparsity, False, opts.diag_scale_polys, rng)
+        if opts.full_smoothing_up_and_down:
+            # the smoother inverts the whole level matrix (AIR_Operators_Setup.F90:115-119, 373-377); the grid
+            # transfers get their own assembled inverse of the (dropped) A_ff (:139-151, 413-427)
+            inv_ff, _ = make_inverse(cur, opts.inverse_type, opts.poly_order, opts.inverse_sparsity_order,
+                                     opts.matrix_free_polys, opts.diag_scale_polys, rng)
+            newton = inv_type in (poly.NEWTON, poly.NEWTON_NO_EXTRA)
+            _, asm = make_inverse(A_ff_drop, inv_type, opts.poly_order, sparsity, newton, opts.diag_scale_polys, rng,
+                                  want_assembled=True)
+        else:
+            inv_ff, asm = make_inverse(A_ff, inv_type, opts.poly_order, sparsity, opts.matrix_free_polys,
+                                       opts.diag_scale_polys, rng, want_assembled=(opts.strong_r_threshold == 0.0))
+            if opts.strong_r_threshold != 0.0:
+                _, asm = make_inverse(A_ff_drop, inv_type, opts.poly_order, sparsity, False, opts.diag_scale_polys, rng)
         if asm is None:
             raise NotImplementedError("grid transfers need an assembled inverse (z_type product)")
         # W
@@ -311,7 +324,9 @@ def build_hierarchy(A, opts: AirOptions = None, verbose=False):
         del RAP
         lv = Level(n=n, is_fine=is_f, is_coarse=is_c, A_ff=_i32(A_ff), A_fc=_i32(A_fc), inv_A_ff=inv_ff,
                    R=R, P=P, smooth_order=smooth, aff_diag=aff_diag)
-        if opts.any_c_smooths:
+        if opts.full_smoothing_up_and_down:
+            lv.A = cur
+        if opts.any_c_smooths and not opts.full_smoothing_up_and_down:
             lv.A_cf = _i32(A_cf)
             lv.A_cc = _i32(_extract(cur, is_c, cmap, nc))
             lv.inv_A_cc, _ = make_inverse(lv.A_cc, opts.c_inverse_type, opts.c_poly_order,

@@ -79,6 +79,11 @@ class OracleAIR:
         im = np.ascontiguousarray(c[:, 1]) if c.shape[1] > 1 else np.zeros_like(re)
         self.L.oracle_set_poly(self.h, our_level, which, inverse_type, re.size, _dp(re), _dp(im), int(diag_scale))
 
+    def set_option(self, key, value):
+        """Options that change the apply (mirrors pflare_b200_set_option); unknown keys are execution-only and ignored."""
+        if key == "full_smoothing_up_and_down":
+            self.L.oracle_set_full_smoothing(self.h, int(bool(value)))
+
     def finalize(self):
         pass
 

@@ -13,6 +13,10 @@
  *   pcmg_kaskade()            PETSc PCMG, PC_MG_KASKADE, as wired by
  *                             src/AIR_MG_Setup.F90:967-1156 (restrict b down, x_L = 0,
  *                             coarse PREONLY solve, interpolate + 1 Richardson sweep up)
+ *   pcmg_multiplicative()     -pc_air_full_smoothing_up_and_down: PETSc PCMG, PC_MG_MULTIPLICATIVE
+ *                             V-cycle, one Richardson/PCMAT sweep with inv_A_ff(level) on ALL
+ *                             unknowns down and up, true residual restriction R (b - A x)
+ *                             (src/AIR_MG_Setup.F90:978-1074, src/AIR_Operators_Setup.F90:115-119)
  *   mg_coarse_shell_apply()   src/FC_Smooth.F90:29-49
  *   mg_fc_point_richardson()  src/FC_Smooth.F90:421-495
  *   f_smooths()               src/FC_Smooth.F90:499-568
@@ -77,9 +81,10 @@ typedef struct {
   inv_t inv_ff, inv_cc;
   double *tf[5], *tc[5]; /* temp_vecs_fine(1:4), temp_vecs_coarse(1:4) */
   double *b, *x;         /* PCMG level vectors */
+  double *r, *z;         /* PCMG residual / Richardson work vectors (full smoothing only) */
 } level_t;
 
-typedef struct { int no_levels; level_t L[MAXLEV]; } hier_t;
+typedef struct { int no_levels; int full_smoothing; level_t L[MAXLEV]; } hier_t;
 
 /* ---------------------------------------------------------------- PETSc primitives */
 static void MatMult(const csr_t *A, const double *x, double *y) {
@@ -285,6 +290,55 @@ static void pcmg_kaskade(hier_t *H, const double *b_in, double *x_out) {
   VecCopy(L[1].n, L[1].x, x_out);
 }
 
+/* MatMultAdd_SeqAIJ(A, x, y, y): the row sum starts from y_i (PETSc: sum = y[i]; sum += a_ij x_j ...) */
+static void MatMultAddInPlace(const csr_t *A, const double *x, double *y) {
+  const int m = A->m;
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < m; ++i) {
+    double s = y[i];
+    for (int p = A->ia[i]; p < A->ia[i + 1]; ++p) s += A->a[p] * x[A->ja[p]];
+    y[i] = s;
+  }
+}
+
+/* -pc_air_full_smoothing_up_and_down (src/AIR_MG_Setup.F90:978-1074): PCMG keeps its default
+ * PC_MG_MULTIPLICATIVE V-cycle (PCMGMCycle_Private of PETSc's mg.c), the level smoothers are
+ * KSPRICHARDSON (1 iteration, KSP_NORM_NONE, scale 1) preconditioned by PCMAT with
+ * inv_A_ff(our_level) -- here an approximate inverse of the WHOLE level matrix
+ * coarse_matrix(our_level) (src/AIR_Operators_Setup.F90:115-119, 373-377):
+ *   down:  x_l = 0 ; x_l += M_l b_l            (pre-smooth; zero guess: r = b)
+ *          r_l = b_l - A_l x_l                  (PCMGResidualDefault)
+ *          b_{l+1} = R_l r_l ; x_{l+1} = 0      (MatRestrict)
+ *   coarsest: x_L = inv_A_ff(L) b_L             (mg_coarse_shell_apply)
+ *   up:    x_l = x_l + P_l x_{l+1}              (MatInterpolateAdd)
+ *          r = b_l - A_l x_l ; x_l += M_l r     (post-smooth; nonzero guess) */
+static void pcmg_multiplicative(hier_t *H, const double *b_in, double *x_out) {
+  const int NL = H->no_levels;
+  level_t *L = H->L;
+  VecCopy(L[1].n, b_in, L[1].b);
+  for (int l = 1; l <= NL - 1; ++l) {
+    const int n = L[l].n;
+    ensure(&L[l].r, n); ensure(&L[l].z, n);
+    VecSet(n, L[l].x, 0.0);
+    inv_mult(&L[l].inv_ff, &L[l].M[W_COARSE], L[l].b, L[l].z);
+    VecAXPY(n, L[l].x, 1.0, L[l].z);
+    MatMult(&L[l].M[W_COARSE], L[l].x, L[l].r);
+    VecAYPX(n, L[l].r, -1.0, L[l].b);
+    MatMult(&L[l].M[W_R], L[l].r, L[l + 1].b);
+  }
+  VecSet(L[NL].n, L[NL].x, 0.0);
+  inv_mult(&L[NL].inv_ff, &L[NL].M[W_COARSE], L[NL].b, L[NL].x);
+  for (int l = NL - 1; l >= 1; --l) {
+    const int n = L[l].n;
+    MatMultAddInPlace(&L[l].M[W_P], L[l + 1].x, L[l].x);
+    MatMult(&L[l].M[W_COARSE], L[l].x, L[l].r);
+    VecAYPX(n, L[l].r, -1.0, L[l].b);
+    inv_mult(&L[l].inv_ff, &L[l].M[W_COARSE], L[l].r, L[l].z);
+    VecAXPY(n, L[l].x, 1.0, L[l].z);
+  }
+  VecCopy(L[1].n, L[1].x, x_out);
+}
+
 /* ---------------------------------------------------------------- construction API */
 static void csr_copy(csr_t *d, int m, int n, const int *ia, const int *ja, const double *a) {
   free(d->ia); free(d->ja); free(d->a);
@@ -361,9 +415,13 @@ int oracle_pcapply(void *h, const double *b, double *x) {
   hier_t *H = (hier_t *)h;
   if (H->no_levels == 1) return 1; /* the reference falls back to PCJACOBI here (AIR_MG_Setup.F90:1167-1174) */
   if (!H->L[H->no_levels].b) return 2; /* oracle_set_level must be called for every level incl. the coarsest */
-  pcmg_kaskade(H, b, x);
+  if (H->full_smoothing) pcmg_multiplicative(H, b, x);
+  else pcmg_kaskade(H, b, x);
   return 0;
 }
+
+/* -pc_air_full_smoothing_up_and_down: inv_A_ff(l) then inverts coarse_matrix(l) (set as W_COARSE on every level) */
+void oracle_set_full_smoothing(void *h, int flag) { ((hier_t *)h)->full_smoothing = flag; }
 
 /* PCApply_PFLAREINV_c: y = mat_inverse * x (src/PCPFLAREINV.c:618-626); also used by tests to
  * exercise any level's inverse on its own.  which = W_INV_AFF (matrix W_AFF, or W_COARSE on
@@ -372,7 +430,7 @@ int oracle_inv_apply(void *h, int our_level, int which, const double *x, double 
   hier_t *H = (hier_t *)h;
   level_t *L = &H->L[our_level];
   inv_t *I = pick_inv(L, which);
-  const csr_t *A = which == W_INV_ACC ? &L->M[W_ACC] : (our_level == H->no_levels ? &L->M[W_COARSE] : &L->M[W_AFF]);
+  const csr_t *A = which == W_INV_ACC ? &L->M[W_ACC] : ((our_level == H->no_levels || H->full_smoothing) ? &L->M[W_COARSE] : &L->M[W_AFF]);
   if (I->kind == 0) return 1;
   inv_mult(I, A, x, y);
   return 0;
@@ -404,7 +462,7 @@ void oracle_destroy(void *h) {
   if (!H) return;
   for (int l = 0; l < MAXLEV; ++l) {
     level_t *L = &H->L[l];
-    free(L->is_f); free(L->is_c); free(L->b); free(L->x);
+    free(L->is_f); free(L->is_c); free(L->b); free(L->x); free(L->r); free(L->z);
     for (int k = 0; k < 5; ++k) { free(L->tf[k]); free(L->tc[k]); }
     for (int w = 0; w < W_COUNT; ++w) { free(L->M[w].ia); free(L->M[w].ja); free(L->M[w].a); }
     inv_free(&L->inv_ff); inv_free(&L->inv_cc);

@@ -5,13 +5,13 @@
 // the fused vector updates.  The path is HBM-bound fp64/int32 work (no tensor cores by design).
 //
 //   spmv_wt_kernel      the kernel of the cycle (round 2).  The operator is stored as WARP TILES: one
-//                       contiguous blob per tile (<= 256 nonzeros of consecutive rows: values, column
-//                       indices, per-lane row-end masks) that ONE 1-D TMA bulk copy brings into a
+//                       contiguous blob per tile (<= 8 slots per lane x 32 lanes of consecutive rows,
+//                       row-aligned lanes: wt_format.h) that ONE 1-D TMA bulk copy brings into a
 //                       per-warp shared-memory ring.  Warps are autonomous (no CTA barrier anywhere):
 //                       while a warp reduces tile t its x gathers and epilogue operands of tile t+1 are
 //                       already in flight in registers and tiles t+2.. are in flight in the ring.  Rows
-//                       are summed by a lane-local walk plus one segmented warp scan; the row epilogue
-//                       is specialised at compile time per op class.
+//                       are summed by lane-local adds plus a segmented shuffle reduction; the row
+//                       epilogue is specialised at compile time per op class.
 //   spmv_tma_kernel     round-1 kernel (CTA tiles of a CSR stream, 3 bulk copies per tile, CTA barriers);
 //                       kept as option kernel=1 for A/B measurements.
 //   spmv_stream_kernel  first-generation smem-staged kernel (option kernel=0); also the fallback for
@@ -53,7 +53,7 @@ struct SpmvOp {
   const unsigned char *blob;
   const WtDesc *wdesc;
   int nwt;
-  int rq;                      // rows per lane of a tile: a tile holds <= 32 * rq rows
+  int kp;                      // slots per lane of a sub-tile (1, 2, 4, 8); a tile holds <= 8 / kp sub-tiles
   int epi;                     // epilogue class
   // gather sources: column c < nloc reads x[c], otherwise xg[c - nloc] (ghost buffer)
   const double *x, *xg;
@@ -331,28 +331,29 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-tile SpMV (the kernel of the cycle).
+// Warp-tile SpMV (the kernel of the cycle).  Operator storage: wt_format.h (row-aligned lanes).
 //
 // Persistent CTAs of NW autonomous warps.  Global warp g owns the tiles g, g + #warps, ...; lane 0
 // keeps STAGES bulk copies (one per tile) in flight into the warp's private ring, each signalled on
 // its own mbarrier.  Per tile the warp runs two software-pipelined stages:
 //   A (one tile ahead)  read the tile's column indices from shared memory and issue the x gathers
 //                       and the loads of the rows' epilogue operands into registers;
-//   B                   products in registers; every lane walks its kpl consecutive nonzeros, a
-//                       segmented warp scan (shuffles) carries the partial sum of a row that spans
-//                       lanes; finished row sums go to shared memory (the consumed value area of the
-//                       stage) so that the epilogue runs with one row per lane (coalesced vector
-//                       traffic), RQ rows per lane for operators with short rows.
+//   B                   products in registers; per sub-tile every lane sums its KP slots and a
+//                       segmented shuffle reduction over the lanes of a row leaves the row sum in
+//                       the row's head lane; row sums go to shared memory (the consumed value area
+//                       of the stage) so that the epilogue runs with one row per lane (coalesced
+//                       vector traffic), 8 / KP rows per lane.
 // No __syncthreads: a warp never waits for another warp, so one warp's gather latency is hidden by
 // the other warps of the SM and the bulk stream never drains.
-template <int EPI, int RQ, bool GHOST, int NW, int STAGES>
+template <int EPI, int KP, bool GHOST, int NW, int STAGES>
 __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
   typedef EpiT<EPI> E;
   typedef typename E::Pre Pre;
   constexpr bool XW = E::kXw;
-  constexpr int KPL = kWtKpl;
-  constexpr bool AHEAD = E::kPre * RQ <= 16;   // epilogue operands prefetched one tile ahead (else at the start of stage B)
-  constexpr int XW_BYTES = XW ? RQ * 32 * 8 : 0;
+  constexpr int NSLOT = kWtSlots;
+  constexpr int NS = kWtSlots / KP;            // sub-tiles per tile == rows per lane in the epilogue
+  constexpr bool AHEAD = E::kPre * NS <= 16;   // epilogue operands prefetched one tile ahead (else at the start of stage B)
+  constexpr int XW_BYTES = XW ? NS * 32 * 8 : 0;
   constexpr int WARP_BYTES = STAGES * kWtStageBytes + XW_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[NW][STAGES];
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
     if (j + 1 < my) dn = wdesc[(size_t)first + (size_t)(j + 1) * nwarps];
     const int slot = j % STAGES;
     sdesc[w][slot] = d;
-    const uint32_t bytes = (uint32_t)(d.kpl * 384 + 64);
+    const uint32_t bytes = (uint32_t)((d.geom & 0xff) * KP * 384 + 32);
     mbar_expect_tx(&full[w][slot], bytes);
     tma_load_1d(wbase + slot * kWtStageBytes, op.blob + (size_t)d.off16 * 16, bytes, &full[w][slot], pol);
   };
@@ -394,18 +395,19 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
   const double *__restrict__ xg = op.xg;
   const int nloc = op.nloc;
   WtDesc dnx = {0u, 0, 0, 0};
-  double xn[KPL];
-  Pre pn[RQ];
+  double xn[NSLOT];
+  Pre pn[NS];
   // stage A of tile j
   auto stage_a = [&](int j) {
     const int slot = j % STAGES;
     mbar_wait(&full[w][slot], (uint32_t)((j / STAGES) & 1));
     dnx = sdesc[w][slot];
-    const int *col_s = reinterpret_cast<const int *>(wbase + slot * kWtStageBytes + dnx.kpl * 256);
+    const int nslots = (dnx.geom & 0xff) * KP;
+    const int *col_s = reinterpret_cast<const int *>(wbase + slot * kWtStageBytes + nslots * 256);
 #pragma unroll
-    for (int k = 0; k < KPL; ++k) {
+    for (int k = 0; k < NSLOT; ++k) {
       xn[k] = 0.0;
-      if (k < dnx.kpl) {
+      if (k < nslots) {
         const int c = col_s[k * 32 + lane];
         if (GHOST) xn[k] = (c >= nloc) ? __ldcg(xg + (c - nloc)) : xv[c];
         else xn[k] = xv[c];
@@ -413,77 +415,78 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
     }
     if (AHEAD) {
 #pragma unroll
-      for (int q = 0; q < RQ; ++q)
+      for (int q = 0; q < NS; ++q)
         if (lane + 32 * q < dnx.nrows) pn[q] = E::prefetch(op, dnx.r0 + lane + 32 * q);
     }
   };
   if (my > 0) stage_a(0);
   for (int it = 0; it < my; ++it) {
     const WtDesc d = dnx;
-    double p[KPL];
-    Pre pc[RQ];
+    double p[NSLOT];
+    Pre pc[NS];
 #pragma unroll
-    for (int k = 0; k < KPL; ++k) p[k] = xn[k];
+    for (int k = 0; k < NSLOT; ++k) p[k] = xn[k];
 #pragma unroll
-    for (int q = 0; q < RQ; ++q) pc[q] = pn[q];
+    for (int q = 0; q < NS; ++q) pc[q] = pn[q];
     if (it + 1 < my) stage_a(it + 1);
     // ---- stage B
     const int slot = it % STAGES;
     unsigned char *st = wbase + slot * kWtStageBytes;
     double *val_s = reinterpret_cast<double *>(st);
+    const int ns = d.geom & 0xff, gmax = d.geom >> 8;
+    const int nslots = ns * KP;
     if (!AHEAD) {
 #pragma unroll
-      for (int q = 0; q < RQ; ++q)
+      for (int q = 0; q < NS; ++q)
         if (lane + 32 * q < d.nrows) pc[q] = E::prefetch(op, d.r0 + lane + 32 * q);
     }
 #pragma unroll
-    for (int k = 0; k < KPL; ++k) p[k] = (k < d.kpl) ? val_s[k * 32 + lane] * p[k] : 0.0;
-    const unsigned e = reinterpret_cast<const unsigned short *>(st + d.kpl * 384)[lane];
+    for (int k = 0; k < NSLOT; ++k) p[k] = (k < nslots) ? val_s[k * 32 + lane] * p[k] : 0.0;
+    const unsigned *heads = reinterpret_cast<const unsigned *>(st + nslots * 384);
+    unsigned hd[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) hd[s] = (s < ns) ? heads[s] : 0u;
     __syncwarp();   // every lane holds its values: the value area now receives the row sums
-    // partial sum after this lane's last row end (the whole lane if it ends no row)
-    const int last = 31 - __clz((int)e);
-    double tail = 0.0;
+    const bool wf = (EPI == EPI_AFCW || EPI == EPI_AFCW_LOCAL) || (EPI == EPI_GENERIC && op.wlast);
+    int rowbase = 0;
 #pragma unroll
-    for (int k = 0; k < KPL; ++k)
-      if (k > last) tail += p[k];
-    // segmented inclusive scan of the tails over the lanes (a lane that ends a row starts a new segment)
-    const unsigned has = __ballot_sync(0xffffffffu, e != 0u);
-    const unsigned upto = has & (0xffffffffu >> (31 - lane));
-    const int dist = lane - (upto ? 31 - __clz((int)upto) : 0);
-    double sc = tail;
+    for (int s = 0; s < NS; ++s) {
+      if (s < ns) {
+        const unsigned H = hd[s];
+        const bool head = (H >> lane) & 1u;
+        double acc = 0.0, xw = 0.0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, sc, o);
-      if (o <= dist) sc += t;
-    }
-    double acc = __shfl_up_sync(0xffffffffu, sc, 1);   // the open row's partial sum entering this lane
-    if (lane == 0) acc = 0.0;
-    // first tile-local row index this lane finishes
-    const int cnt = __popc(e);
-    int rb = cnt;
+        for (int j = 0; j < KP; ++j) {
+          if (XW && j == 0) {
+            if (wf && head) xw = p[s * KP];   // merged A_fc|W: the row's first entry is the W entry
+            else acc += p[s * KP];
+          } else {
+            acc += p[s * KP + j];
+          }
+        }
+        // segmented reduction over the lanes of a row (toward its head lane)
+        const unsigned above = lane < 31 ? (H >> (lane + 1)) : 0u;
+        const int dist = above ? __ffs((int)above) - 1 : 31 - lane;   // lanes of my row after me
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, rb, o);
-      if (lane >= o) rb += t;
-    }
-    rb -= cnt;
-    const bool wl = (EPI == EPI_AFCW || EPI == EPI_AFCW_LOCAL) || (EPI == EPI_GENERIC && op.wlast);
-#pragma unroll
-    for (int k = 0; k < KPL; ++k) {
-      const bool end = (e >> k) & 1u;
-      if (XW && wl) {
-        if (end) { val_s[rb] = acc; xw_s[rb] = p[k]; ++rb; acc = 0.0; }
-        else acc += p[k];
-      } else {
-        acc += p[k];
-        if (end) { val_s[rb] = acc; ++rb; acc = 0.0; }
+        for (int o = 1; o < 32; o <<= 1) {
+          if (o < gmax) {
+            const double t = __shfl_down_sync(0xffffffffu, acc, o);
+            if (o <= dist) acc += t;
+          }
+        }
+        if (head) {
+          const int r = rowbase + __popc(H & ((1u << lane) - 1u));
+          val_s[r] = acc;
+          if (XW && wf) xw_s[r] = xw;
+        }
+        rowbase += __popc(H);
       }
     }
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < RQ; ++q) {
+    for (int q = 0; q < NS; ++q) {
       const int r = lane + 32 * q;
-      if (r < d.nrows) E::finish(op, d.r0 + r, val_s[r], (XW && wl) ? xw_s[r] : 0.0, pc[q]);
+      if (r < d.nrows) E::finish(op, d.r0 + r, val_s[r], (XW && wf) ? xw_s[r] : 0.0, pc[q]);
     }
     // generic-proxy accesses to this slot are done; order them before the next bulk copy into it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

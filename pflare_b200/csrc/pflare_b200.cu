@@ -120,7 +120,7 @@ struct DevCSR {
   // warp-tile storage (kernel 2): one blob per tile + descriptor list, interior tiles first
   unsigned char *blob = nullptr;
   WtDesc *wdesc = nullptr;
-  int nwt = 0, nwt_int = 0, rq = 1;
+  int nwt = 0, nwt_int = 0, kp = 8;
   bool wt = false;         // this operator runs on the warp-tile kernel (no row longer than a tile)
   DevPlan *xp = nullptr;   // ghost exchange (multi-rank)
   bool is_set = false;
@@ -146,13 +146,14 @@ struct Level {
   Inv inv_ff, inv_cc;
   // device
   DevCSR Z, W, Afc, Afcw, Aff, Acf, Acc, Coarse;   // Afcw = A_fc with the one-point W entry appended to every row
+  DevCSR Pn;                   // full smoothing: P = [W; I] in nested ordering (x_l += P x_{l+1}); Coarse = A_l on every level
   bool w_onepoint = false;
   bool aff_diag_only = false;
   double *aff_diag = nullptr;  // diagonal of A_ff (F-local order): MF_VEC_DIAG and the fused local smooth
   double *acc_diag = nullptr;  // diagonal of A_cc (nested order)
   double *coarse_diag = nullptr;
   double *bc_save = nullptr;   // copy of b_c when the level has C smooths
-  int64_t off = 0;             // offset of this level's vector in the nested arrays
+  int64_t xoff = 0, boff = 0;  // offsets of this level's x / b vector in the nested arrays (equal in the Kaskade cycle)
   std::vector<int> pos;        // natural index -> nested position (relative to off)
   std::vector<int> fpos;       // natural index -> F-local index or -1
   int *d_pos = nullptr, *d_inv = nullptr;
@@ -205,9 +206,10 @@ struct Ctx {
   // options
   int use_graph = 1, fuse = 1;
   int fuse_epi = 1;      // compile-time specialised epilogue classes (0: every op runs the generic epilogue)
+  int full_smooth = 0;   // -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1), inv_A_ff(l) ~ A_l^-1 on all unknowns
   int dense_rows = 4096; // levels with <= this many rows are collapsed into one dense matrix (0 = off)
   int kernel = 2;        // 0: smem-staged stream kernel, 1: round-1 TMA kernel (CTA tiles), 2: warp-tile kernel
-  int wt_stages = 3;     // ring depth of the warp-tile kernel (3 or 4 tiles per warp)
+  int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
   int pdl = 1;           // programmatic dependent launch between the kernels of the cycle
@@ -289,7 +291,7 @@ int dev_upload_padded(Ctx *c, T **p, const std::vector<T> &v, size_t pad) {
 
 // Upload one device-ordered operator.  h.n = local columns; ghost columns (if any) are numbered
 // h.n .. h.n + h.n_ghost - 1 inside h.ja and described by h.garray (global ids in `space`).
-int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int space_level = 0) {
+int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int space_level = 0, bool wfirst = false) {
   if (h.nnz() >= (int64_t)2147483647) return fail(3, "operator has >= 2^31 nonzeros (32-bit PetscInt only)");
   d->m = h.m;
   d->n = h.n;
@@ -316,9 +318,9 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int s
   d->wt = false;
   if (c->kernel == 2) {
     WtHost W;
-    build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), &W);
+    build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), wfirst, &W);
     if (W.ok) {
-      d->wt = true; d->rq = W.rq;
+      d->wt = true; d->kp = W.kp;
       d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
       if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
       if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
@@ -434,7 +436,7 @@ struct Builder {
     SpmvOp s{};
     s.rp = A.rp; s.col = A.col; s.val = A.val; s.m = A.m; s.nblk = A.nblk; s.blk = A.blk;
     s.tiles = A.tiles; s.ntiles = A.ntiles;
-    s.blob = A.blob; s.wdesc = A.wdesc; s.nwt = A.wt ? A.nwt : 0; s.rq = A.rq;
+    s.blob = A.blob; s.wdesc = A.wdesc; s.nwt = A.wt ? A.nwt : 0; s.kp = A.kp;
     s.x = x; s.nloc = A.n; s.beta = 1.0;
     s.xg = A.xp ? A.xp->d_xg : nullptr;
     return s;
@@ -625,7 +627,7 @@ struct Builder {
   }
 
   int emit_f_smooths(Level &Lv, bool first_smooth, bool prolong_pending, int its) {
-    double *xb = c->xb + Lv.off, *bb = c->bb + Lv.off;
+    double *xb = c->xb + Lv.xoff, *bb = c->bb + Lv.boff;
     double *xf = xb, *xc = xb + Lv.nf;
     const double *bf = bb;
     double **S = c->scr;
@@ -664,7 +666,7 @@ struct Builder {
   }
 
   int emit_c_smooths(Level &Lv, bool prolong_pending, int its) {
-    double *xb = c->xb + Lv.off;
+    double *xb = c->xb + Lv.xoff;
     double *xf = xb, *xc = xb + Lv.nf;
     double **S = c->scr;
     if (prolong_pending) emit_prolong(Lv, xf, xc);
@@ -697,7 +699,7 @@ struct Builder {
       first = false;
       pending = false;
     }
-    if (pending) emit_prolong(Lv, c->xb + Lv.off, c->xb + Lv.off + Lv.nf);
+    if (pending) emit_prolong(Lv, c->xb + Lv.xoff, c->xb + Lv.xoff + Lv.nf);
     return 0;
   }
 };
@@ -846,10 +848,10 @@ int launch_r1(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
 }
 
 // warp-tile kernel: one instantiation per (epilogue class, rows per lane, ghost columns, ring depth)
-template <int EPI, int RQ, bool GH, int ST>
+template <int EPI, int KP, bool GH, int ST>
 int launch_wt_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_wt_kernel<EPI, RQ, GH, kWtWarps, ST>;
-  const size_t smem = (size_t)kWtWarps * (ST * kWtStageBytes + (EpiT<EPI>::kXw ? RQ * 32 * 8 : 0));
+  auto kern = spmv_wt_kernel<EPI, KP, GH, kWtWarps, ST>;
+  const size_t smem = (size_t)kWtWarps * (ST * kWtStageBytes + (EpiT<EPI>::kXw ? (kWtSlots / KP) * 32 * 8 : 0));
   static int per_sm = 0;
   int rc = kernel_per_sm(kern, kWtWarps * 32, smem, &per_sm);
   if (rc || dry) return rc;
@@ -859,22 +861,21 @@ int launch_wt_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   CUDA_TRY(launch_k(c->pdl != 0, kern, grid, kWtWarps * 32, smem, st, s));
   return 0;
 }
-template <int EPI, int RQ>
-int launch_wt_rq(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+template <int EPI, int KP>
+int launch_wt_kp(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   const bool gh = s.xg != nullptr;
-  if (c->wt_stages == 4) return gh ? launch_wt_inst<EPI, RQ, true, 4>(c, s, st, dry) : launch_wt_inst<EPI, RQ, false, 4>(c, s, st, dry);
-  if (c->wt_stages == 2) return gh ? launch_wt_inst<EPI, RQ, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, RQ, false, 2>(c, s, st, dry);
-  return gh ? launch_wt_inst<EPI, RQ, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, RQ, false, 3>(c, s, st, dry);
+  if (c->wt_stages == 3) return gh ? launch_wt_inst<EPI, KP, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 3>(c, s, st, dry);
+  return gh ? launch_wt_inst<EPI, KP, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 2>(c, s, st, dry);
 }
 template <int EPI>
 int launch_wt_epi(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  switch (s.rq) {
-    case 1: return launch_wt_rq<EPI, 1>(c, s, st, dry);
-    case 2: return launch_wt_rq<EPI, 2>(c, s, st, dry);
-    case 4: return launch_wt_rq<EPI, 4>(c, s, st, dry);
-    case 8: return launch_wt_rq<EPI, 8>(c, s, st, dry);
+  switch (s.kp) {
+    case 1: return launch_wt_kp<EPI, 1>(c, s, st, dry);
+    case 2: return launch_wt_kp<EPI, 2>(c, s, st, dry);
+    case 4: return launch_wt_kp<EPI, 4>(c, s, st, dry);
+    case 8: return launch_wt_kp<EPI, 8>(c, s, st, dry);
   }
-  return fail(7, "internal: rows-per-lane %d", s.rq);
+  return fail(7, "internal: slots per lane %d", s.kp);
 }
 int launch_wt(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   switch (s.epi) {
@@ -1059,14 +1060,14 @@ int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op
           Ctx *c = R[r];
           const Level &LB = c->L[c->l_agg];
           if (!LB.n) continue;
-          double *piece = (gather ? c->bb : c->xb) + LB.off;
+          double *piece = gather ? c->bb + LB.boff : c->xb + LB.xoff;
           double *glob = (gather ? c0->child_b : c0->child_x) + c0->rangeV[c0->l_agg].start[r];
           CUDA_TRY(cudaMemcpyAsync(gather ? glob : piece, gather ? piece : glob, (size_t)LB.n * 8, cudaMemcpyDeviceToDevice, st));
         }
       } else {
         Ctx *c = R[0];
         const Level &LB = c->L[c->l_agg];
-        double *piece = (gather ? c->bb : c->xb) + LB.off;
+        double *piece = gather ? c->bb + LB.boff : c->xb + LB.xoff;
         std::string err;
         bool ok = true;
         if (c->rank == 0) {
@@ -1145,14 +1146,36 @@ int build_program(Ctx *c) {
     for (int l = NL; l >= 1; --l) { if (c->L[l].n <= c->dense_rows) ldense = l; else break; }
     if (ldense > NL - 1) ldense = NL + 1;   // >= 2 levels
   }
-  // down: b_{l+1} = b_c + Z b_f  (MatRestrict with R = [Z I])
-  for (int l = 1; l <= LB - 1; ++l) {
+  // -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1) (src/AIR_MG_Setup.F90:978-1074), going down
+  //   x_l = M_l b_l (Richardson from a zero guess) ; r_l = b_l - A_l x_l ; b_{l+1} = R r_l = r_c + Z r_f
+  // A_l is streamed once for the residual (its C rows are written straight into b_{l+1}), Z once.
+  for (int l = 1; c->full_smooth && l <= LB - 1; ++l) {
     Level &Lv = c->L[l];
     B.level = l;
     if (l == ldense) dense_begin = (int)c->prog.size();
-    if (Lv.any_c) B.push_ew(Lv.nc, c->bb + Lv.off + Lv.nf, nullptr, nullptr, 1.0, Lv.bc_save, 1);
-    SpmvOp s = B.base(Lv.Z, c->bb + Lv.off);
-    s.out = c->bb + Lv.off + Lv.nf; s.out_mode = 2;
+    double *xl = c->xb + Lv.xoff, *bl = c->bb + Lv.boff, *rl = bl + Lv.n;
+    int rc = B.emit_inv(Lv.inv_ff, Lv.Coarse, Lv.coarse_diag, Lv.n, bl, xl, 1);
+    if (rc) return rc;
+    {
+      SpmvOp s = B.base(Lv.Coarse, xl);
+      s.aux = bl; s.alpha = 1.0; s.beta = -1.0;
+      s.out = rl; s.out_mode = 1;
+      B.push_spmv(s, Lv.Coarse, 4, 1, 1);
+    }
+    {
+      SpmvOp s = B.base(Lv.Z, rl);
+      s.out = rl + Lv.nf; s.out_mode = 2;
+      B.push_spmv(s, Lv.Z, 1, 0, 2);
+    }
+  }
+  // down: b_{l+1} = b_c + Z b_f  (MatRestrict with R = [Z I])
+  for (int l = 1; !c->full_smooth && l <= LB - 1; ++l) {
+    Level &Lv = c->L[l];
+    B.level = l;
+    if (l == ldense) dense_begin = (int)c->prog.size();
+    if (Lv.any_c) B.push_ew(Lv.nc, c->bb + Lv.boff + Lv.nf, nullptr, nullptr, 1.0, Lv.bc_save, 1);
+    SpmvOp s = B.base(Lv.Z, c->bb + Lv.boff);
+    s.out = c->bb + Lv.boff + Lv.nf; s.out_mode = 2;
     B.push_spmv(s, Lv.Z, 1, 0, 2);
   }
   if (agg) {
@@ -1165,14 +1188,34 @@ int build_program(Ctx *c) {
     // coarse solve: x_L = inv_A_ff(L) b_L  (mg_coarse_shell_apply, src/FC_Smooth.F90:29-49)
     Level &Lv = c->L[NL];
     B.level = NL;
-    int rc = B.emit_inv(Lv.inv_ff, Lv.Coarse, Lv.coarse_diag, Lv.n, c->bb + Lv.off, c->xb + Lv.off, 1);
+    int rc = B.emit_inv(Lv.inv_ff, Lv.Coarse, Lv.coarse_diag, Lv.n, c->bb + Lv.boff, c->xb + Lv.xoff, 1);
     if (rc) return rc;
   }
   // up: x_l = P x_{l+1}; one mg_FC_point_richardson
-  for (int l = LB - 1; l >= 1; --l) {
+  for (int l = LB - 1; !c->full_smooth && l >= 1; --l) {
     Level &Lv = c->L[l];
     B.level = l;
     int rc = B.emit_fc_richardson(Lv, true);
+    if (rc) return rc;
+    if (l == ldense) dense_end = (int)c->prog.size();
+  }
+  // full smoothing, going up: x_l += P x_{l+1} (MatInterpolateAdd) ; x_l += M_l (b_l - A_l x_l)
+  for (int l = LB - 1; c->full_smooth && l >= 1; --l) {
+    Level &Lv = c->L[l];
+    B.level = l;
+    double *xl = c->xb + Lv.xoff, *bl = c->bb + Lv.boff;
+    {
+      SpmvOp s = B.base(Lv.Pn, c->xb + c->L[l + 1].xoff);
+      s.out = xl; s.out_mode = 2;
+      B.push_spmv(s, Lv.Pn, 3, 0, 2);
+    }
+    {
+      SpmvOp s = B.base(Lv.Coarse, xl);
+      s.aux = bl; s.alpha = 1.0; s.beta = -1.0;
+      s.out = c->scr[1]; s.out_mode = 1;
+      B.push_spmv(s, Lv.Coarse, 4, 1, 1);
+    }
+    int rc = B.emit_inv(Lv.inv_ff, Lv.Coarse, Lv.coarse_diag, Lv.n, c->scr[1], xl, 2);
     if (rc) return rc;
     if (l == ldense) dense_end = (int)c->prog.size();
   }
@@ -1182,7 +1225,7 @@ int build_program(Ctx *c) {
     Level &Ld = c->L[ldense];
     std::vector<Op> sub(c->prog.begin() + dense_begin, c->prog.begin() + dense_end);
     Op d; d.kind = OPK_DENSE; d.level = ldense; d.tag = 11;
-    d.e.n = Ld.n; d.e.a = c->bb + Ld.off; d.e.out = c->xb + Ld.off;
+    d.e.n = Ld.n; d.e.a = c->bb + Ld.boff; d.e.out = c->xb + Ld.xoff;
     for (const Op &o : sub) { d.bytes += o.bytes; d.nnz += o.nnz; }
     c->prog.erase(c->prog.begin() + dense_begin, c->prog.begin() + dense_end);
     c->prog.insert(c->prog.begin() + dense_begin, d);
@@ -1225,9 +1268,9 @@ int build_dense_tail(Ctx *c) {
   std::vector<const std::vector<Op> *> P{&c->dense_prog};
   const int grid = std::min((n + kThreads - 1) / kThreads, c->num_sms * 8);
   for (int j = 0; j < n; ++j) {
-    unit_vector_kernel<<<grid, kThreads, 0, c->stream>>>(n, j, c->bb + Ld.off);
+    unit_vector_kernel<<<grid, kThreads, 0, c->stream>>>(n, j, c->bb + Ld.boff);
     if ((rc = exec_ops(R, P, 0, (int)c->dense_prog.size(), c->stream))) return rc;
-    store_column_kernel<<<grid, kThreads, 0, c->stream>>>(n, j, c->xb + Ld.off, c->dense_T);
+    store_column_kernel<<<grid, kThreads, 0, c->stream>>>(n, j, c->xb + Ld.xoff, c->dense_T);
     if ((j & 255) == 255) CUDA_TRY(cudaStreamSynchronize(c->stream));   // bound the launch queue
   }
   CUDA_TRY(cudaGetLastError());
@@ -1302,7 +1345,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->rank = 0; ch->nranks = 1; ch->device = c->device; ch->no_levels = NL - LA + 1;
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
-  ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
+  ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->full_smooth = c->full_smooth; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   ch->kernel = c->kernel; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
@@ -1367,7 +1410,8 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
     for (int s : Lv.smooth) { if (s == 0) break; if (s < 0) Lv.any_c = true; }
     auto column_count = [&](int w) -> int {
       switch (w) {
-        case PFLARE_B200_AFF: case PFLARE_B200_ACF: case PFLARE_B200_INV_AFF: return cl == ch->no_levels ? Lv.n : Lv.nf;
+        case PFLARE_B200_INV_AFF: if (c->full_smooth) return Lv.n;   // fall through
+        case PFLARE_B200_AFF: case PFLARE_B200_ACF: return cl == ch->no_levels ? Lv.n : Lv.nf;
         case PFLARE_B200_AFC: case PFLARE_B200_ACC: case PFLARE_B200_P: case PFLARE_B200_INV_ACC: return Lv.nc;
         default: return Lv.n;  // R, COARSE
       }
@@ -1478,7 +1522,7 @@ void release_device_state(Ctx *c) {
   c->child_b = c->child_x = nullptr;
   c->arena = nullptr; c->arena_bytes = 0; c->p2p_ready = false; c->d_peer_flags = nullptr; c->d_done = nullptr;
   for (Level &Lv : c->L) {
-    for (DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.inv_ff.d, &Lv.inv_cc.d}) *A = DevCSR();
+    for (DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.Pn, &Lv.inv_ff.d, &Lv.inv_cc.d}) *A = DevCSR();
     Lv.inv_ff.ddiag = Lv.inv_cc.ddiag = nullptr;
     Lv.aff_diag = Lv.acc_diag = Lv.coarse_diag = Lv.bc_save = nullptr;
     Lv.d_pos = Lv.d_inv = nullptr;
@@ -1504,6 +1548,12 @@ int finalize_ctx(Ctx *c) {
     Level &Lv = c->L[l];
     const HostCSR &Pm = Lv.H[PFLARE_B200_P], &Aff = Lv.H[PFLARE_B200_AFF];
     if (!Pm.set || Pm.m != Lv.n) return fail(2, "level %d: prolongator missing or wrong shape", l);
+    if (c->full_smooth) {
+      const HostCSR &Al = Lv.H[PFLARE_B200_COARSE];
+      if (!Al.set || Al.m != Lv.n || Al.n != Lv.n) return fail(2, "level %d: full smoothing needs coarse_matrix(level) (PFLARE_B200_COARSE)", l);
+      affdiag[l] = 0;
+      continue;
+    }
     if (!Aff.set || Aff.m != Lv.nf) return fail(2, "level %d: A_ff missing or wrong shape", l);
     for (int j = 0; j < Lv.nf && onept[l]; ++j) {
       const int i = Lv.is_f[j];
@@ -1593,8 +1643,14 @@ int finalize_ctx(Ctx *c) {
     }
     c->maxn = std::max(c->maxn, Lv.n);
   }
-  c->L[1].off = 0;
-  for (int l = 1; l < LB; ++l) c->L[l + 1].off = c->L[l].off + c->L[l].nf;
+  // Kaskade cycle: x_c(l) and x_{l+1} (b_c(l), b_{l+1}) are the same memory.  Full smoothing keeps every level's
+  // x_l and b_l: X = [x_1 | x_2 | ...], B = [b_1 | r_f(1) | b_2 | r_f(2) | b_3 ...] so that the residual
+  // r_l = b_l - A_l x_l, written at b_l + n_l, drops its C part straight into b_{l+1}.
+  c->L[1].xoff = c->L[1].boff = 0;
+  for (int l = 1; l < LB; ++l) {
+    c->L[l + 1].xoff = c->L[l].xoff + (c->full_smooth ? c->L[l].n : c->L[l].nf);
+    c->L[l + 1].boff = c->L[l].boff + (c->full_smooth ? c->L[l].n + c->L[l].nf : c->L[l].nf);
+  }
 
   // ---- (2) operators of the distributed levels
   for (int l = 1; l <= LB; ++l) {
@@ -1630,6 +1686,33 @@ int finalize_ctx(Ctx *c) {
         const bool extra = Pm.n_ghost > 0 && Pm.oia[i + 1] > Pm.oia[i];
         if (extra || Pm.ia[i + 1] - Pm.ia[i] != 1 || Pm.ja[Pm.ia[i]] != k || Pm.a[Pm.ia[i]] != 1.0)
           return fail(5, "level %d: prolongator C row %d is not an identity row", l, k);
+      }
+      if (c->full_smooth) {
+        // x_l += P x_{l+1} (MatInterpolateAdd): P kept whole, rows and columns in nested order
+        {
+          HostCSR Pn = remap(Pm, Lv.pos.data(), pc.data(), Lv.nc);
+          if ((rc = upload_csr(c, Pn, &Lv.Pn, SP_VNEST, l + 1))) return rc;
+        }
+        // the level matrix and its approximate inverse act on ALL unknowns of the level
+        {
+          HostCSR A2 = remap(Lv.H[PFLARE_B200_COARSE], Lv.pos.data(), Lv.pos.data(), Lv.n);
+          if (c->device >= 0 && (rc = dev_upload(c, &Lv.coarse_diag, extract_diag(A2)))) return rc;
+          if ((rc = upload_csr(c, A2, &Lv.Coarse, SP_VNEST, l))) return rc;
+        }
+        Inv &I = Lv.inv_ff;
+        if (I.kind == 1) {
+          if (I.h.m != Lv.n || I.h.n != Lv.n) return fail(2, "level %d: full smoothing: inv_A_ff must have the shape of coarse_matrix(level)", l);
+          HostCSR M2 = remap(I.h, Lv.pos.data(), Lv.pos.data(), Lv.n);
+          if ((rc = upload_csr(c, M2, &I.d, SP_VNEST, l))) return rc;
+        } else if (I.kind == 2) {
+          if ((int)I.hdiag.size() != Lv.n) return fail(2, "level %d: diagonal inv_A_ff has the wrong size", l);
+          std::vector<double> d2((size_t)Lv.n);
+          for (int k = 0; k < Lv.n; ++k) d2[Lv.pos[k]] = I.hdiag[k];
+          if (c->device >= 0 && (rc = dev_upload(c, &I.ddiag, d2))) return rc;
+        } else if (I.kind == 0) {
+          return fail(2, "level %d: inv_A_ff not set", l);
+        }
+        continue;
       }
       HostCSR Wn; Wn.set = true; Wn.m = Lv.nf; Wn.n = Lv.nc; Wn.ia.assign((size_t)Lv.nf + 1, 0);
       const bool pg = Pm.n_ghost > 0;
@@ -1681,7 +1764,7 @@ int finalize_ctx(Ctx *c) {
         }
         if (Lv.nc == 0 && M.n_ghost == 0)   // no column to point the padding entry at
           for (size_t k = 0; k < M.ja.size(); ++k) M.ja[k] = 0;
-        if ((rc = upload_csr(c, M, &Lv.Afcw, SP_VNEST, l + 1))) return rc;
+        if ((rc = upload_csr(c, M, &Lv.Afcw, SP_VNEST, l + 1, true))) return rc;
         Lv.Afcw.nnz_model = Afc2.nnz() + W.nnz();
       }
       {
@@ -1819,15 +1902,15 @@ int finalize_ctx(Ctx *c) {
   }
 
   // ---- (3) vectors
-  const size_t n1 = (size_t)c->L[1].n;
+  const size_t n1 = (size_t)(c->L[LB].xoff + c->L[LB].n), nb1 = (size_t)(c->L[LB].boff + c->L[LB].n);
   if ((rc = dev_alloc(c, &c->xb, n1 + 8))) return rc;   // + padding: the A_fc|W padding entry may point one past an empty C block
-  if ((rc = dev_alloc(c, &c->bb, n1 + 8))) return rc;
+  if ((rc = dev_alloc(c, &c->bb, nb1 + 8))) return rc;
   for (int k = 0; k < 7; ++k)
     if ((rc = dev_alloc(c, &c->scr[k], (size_t)c->maxn))) return rc;
   if ((rc = dev_alloc(c, &c->io_b, (size_t)c->maxn))) return rc;
   if ((rc = dev_alloc(c, &c->io_x, (size_t)c->maxn))) return rc;
   CUDA_TRY(cudaMemset(c->xb, 0, (n1 + 8) * 8));
-  CUDA_TRY(cudaMemset(c->bb, 0, (n1 + 8) * 8));
+  CUDA_TRY(cudaMemset(c->bb, 0, (nb1 + 8) * 8));
   {
     Level &L1 = c->L[1];
     std::vector<int> inv((size_t)L1.n);
@@ -1914,7 +1997,12 @@ int build_inv_ops(Ctx *c, int our_level, int which, std::vector<Op> *ops, int *n
   const Inv *I; const DevCSR *A; const double *Ad; int n;
   *perm = *iperm = nullptr;
   int rc;
-  if (which == PFLARE_B200_INV_AFF) {
+  if (which == PFLARE_B200_INV_AFF && c->full_smooth && !coarse) {
+    // full smoothing: inv_A_ff(level) acts on all unknowns of the level (natural <-> nested permutation needed)
+    I = &Lv.inv_ff; A = &Lv.Coarse; Ad = Lv.coarse_diag; n = Lv.n;
+    if ((rc = ensure_level_perm(c, Lv))) return rc;
+    *perm = Lv.d_pos; *iperm = Lv.d_inv;
+  } else if (which == PFLARE_B200_INV_AFF) {
     I = &Lv.inv_ff; A = coarse ? &Lv.Coarse : &Lv.Aff; Ad = coarse ? Lv.coarse_diag : Lv.aff_diag; n = coarse ? Lv.n : Lv.nf;
   } else if (which == PFLARE_B200_INV_ACC) {
     if (coarse) return fail(2, "no inv_A_cc on the coarsest level");
@@ -2077,7 +2165,7 @@ int pflare_b200_inv_apply(void *handle, int our_level, int which, const double *
   if (!c->finalized) return fail(6, "inv_apply called before finalize_setup");
   if (c->cluster) return fail(2, "this handle belongs to an in-process rank group: call pflare_b200_cluster_inv_apply");
   const int n_guess = (our_level >= 1 && our_level <= c->no_levels)
-                          ? (which == PFLARE_B200_INV_ACC ? c->L[our_level].nc : (our_level == c->no_levels ? c->L[our_level].n : c->L[our_level].nf)) : 0;
+                          ? (which == PFLARE_B200_INV_ACC ? c->L[our_level].nc : ((our_level == c->no_levels || c->full_smooth) ? c->L[our_level].n : c->L[our_level].nf)) : 0;
   const double *xd = x; double *yd = y;
   if (!on_device) {
     if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);
@@ -2086,7 +2174,7 @@ int pflare_b200_inv_apply(void *handle, int our_level, int which, const double *
   }
   std::vector<Op> ops;
   int n = 0; const int *perm, *iperm;
-  const bool direct = which == PFLARE_B200_INV_AFF;   // no permutation: run on the caller's (or the staging) vectors in place
+  const bool direct = which == PFLARE_B200_INV_AFF && !(c->full_smooth && our_level < c->no_levels);   // no permutation: run on the caller's (or the staging) vectors in place
   if ((rc = build_inv_ops(c, our_level, which, &ops, &n, &perm, &iperm, direct ? xd : nullptr, direct ? yd : nullptr))) return rc;
   if (!direct && (rc = launch_ew_now(c, n, xd, c->bb, iperm, nullptr, c->stream))) return rc;
   std::vector<Ctx *> R{c};
@@ -2107,6 +2195,7 @@ int pflare_b200_fc_smooth(void *handle, int our_level, const double *b, double *
   if (c->cluster) return fail(2, "fc_smooth is not available on an in-process rank group");
   const int LB = c->l_agg <= c->no_levels ? c->l_agg : c->no_levels;
   if (our_level < 1 || our_level >= LB) return fail(2, "fc_smooth: our_level %d has no smoother on this context", our_level);
+  if (c->full_smooth) return fail(2, "fc_smooth: with full_smoothing_up_and_down the level smoother is a plain Richardson sweep with inv_A_ff (use inv_apply)");
   Level &Lv = c->L[our_level];
   if ((rc = ensure_level_perm(c, Lv))) return rc;
   const double *bd = b; double *xd = x;
@@ -2115,17 +2204,17 @@ int pflare_b200_fc_smooth(void *handle, int our_level, const double *b, double *
     CUDA_TRY(cudaMemcpyAsync(c->io_x, x, (size_t)Lv.n * 8, cudaMemcpyHostToDevice, c->stream));
     bd = c->io_b; xd = c->io_x;
   }
-  if ((rc = launch_ew_now(c, Lv.n, bd, c->bb + Lv.off, Lv.d_inv, nullptr, c->stream))) return rc;
-  if ((rc = launch_ew_now(c, Lv.n, xd, c->xb + Lv.off, Lv.d_inv, nullptr, c->stream))) return rc;
+  if ((rc = launch_ew_now(c, Lv.n, bd, c->bb + Lv.boff, Lv.d_inv, nullptr, c->stream))) return rc;
+  if ((rc = launch_ew_now(c, Lv.n, xd, c->xb + Lv.xoff, Lv.d_inv, nullptr, c->stream))) return rc;
   std::vector<Op> ops;
   Builder B{c, &ops};
   B.level = our_level;
-  if (Lv.any_c) B.push_ew(Lv.nc, c->bb + Lv.off + Lv.nf, nullptr, nullptr, 1.0, Lv.bc_save, 1);
+  if (Lv.any_c) B.push_ew(Lv.nc, c->bb + Lv.boff + Lv.nf, nullptr, nullptr, 1.0, Lv.bc_save, 1);
   if ((rc = B.emit_fc_richardson(Lv, false))) return rc;
   std::vector<Ctx *> R{c};
   std::vector<const std::vector<Op> *> Pp{&ops};
   if ((rc = exec_ops(R, Pp, 0, (int)ops.size(), c->stream))) return rc;
-  if ((rc = launch_ew_now(c, Lv.n, c->xb + Lv.off, xd, Lv.d_pos, nullptr, c->stream))) return rc;
+  if ((rc = launch_ew_now(c, Lv.n, c->xb + Lv.xoff, xd, Lv.d_pos, nullptr, c->stream))) return rc;
   if (!on_device) {
     CUDA_TRY(cudaMemcpyAsync(x, c->io_x, (size_t)Lv.n * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -2274,8 +2363,12 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   if (k == "graph") c->use_graph = value != 0;
   else if (k == "fuse") c->fuse = value != 0;
   else if (k == "epi_classes") c->fuse_epi = value != 0;
+  else if (k == "full_smoothing_up_and_down") {
+    if (c->finalized || c->planned) return fail(2, "full_smoothing_up_and_down must be set before finalize_setup");
+    c->full_smooth = value != 0;
+  }
   else if (k == "wt_stages") {
-    if (value != 2 && value != 3 && value != 4) return fail(2, "wt_stages must be 2, 3 or 4");
+    if (value != 2 && value != 3) return fail(2, "wt_stages must be 2 or 3");
     c->wt_stages = (int)value;
   }
   else if (k == "dense_rows") {

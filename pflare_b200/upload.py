@@ -20,9 +20,20 @@ def _feed_inverse(sink, our_level, which, inv):
 
 def feed(H, sink):
     NL = H.no_levels
+    full = bool(getattr(getattr(H, "options", None), "full_smoothing_up_and_down", False))
+    if full:
+        # -pc_air_full_smoothing_up_and_down: the smoother is inv_A_ff(level) applied to coarse_matrix(level) on all
+        # unknowns (src/AIR_MG_Setup.F90:1014-1074): the hook hands over coarse_matrix, inv_A_ff, R and P per level
+        sink.set_option("full_smoothing_up_and_down", 1)
     for l, lv in enumerate(H.levels):
         ol = l + 1
         sink.set_level(ol, lv.n, lv.is_fine, lv.is_coarse, lv.smooth_order)
+        if full:
+            sink.set_csr(ol, COARSE, lv.A)
+            _feed_inverse(sink, ol, INV_AFF, lv.inv_A_ff)
+            sink.set_csr(ol, R, lv.R)
+            sink.set_csr(ol, P, lv.P)
+            continue
         sink.set_csr(ol, AFF, lv.A_ff)
         sink.set_csr(ol, AFC, lv.A_fc)
         if lv.A_cf is not None and lv.A_cc is not None:

@@ -1,8 +1,8 @@
 // wt_format_check.cpp -- CPU check of the warp-tile operator storage (pflare_b200/csrc/wt_format.h) and of
 // the row-sum algorithm spmv_wt_kernel runs on it (pflare_b200/csrc/kernels.cuh, stage B): the 32 lanes of a
 // warp are emulated with arrays, shuffles with indexed reads.  Test infrastructure only (no GPU needed):
-// it pins the layout (lane-interleaved values / columns, per-lane row-end masks, explicit zero for empty
-// rows, interior tiles first) and the segmented-scan logic against a plain CSR product on random matrices.
+// it pins the layout (row-aligned lanes, sub-tiles, head masks, W entry first, explicit zero for empty
+// rows, interior tiles first) and the segmented-reduction logic against a plain CSR product on random matrices.
 //
 //   g++ -O2 -std=c++17 -fopenmp -o wt_format_check wt_format_check.cpp && ./wt_format_check
 #include <cmath>
@@ -15,59 +15,50 @@
 
 using namespace pfb;
 
-static int clz32(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static int ffs32(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 
-// one tile, exactly the steps of the kernel (products -> tails -> segmented scan -> row walk)
-static void tile_rows(const WtHost &W, const WtDesc &d, const std::vector<double> &x, bool wlast, std::vector<double> &rowsum,
+// one tile, exactly the steps of the kernel's stage B (products -> lane sums -> segmented shuffle reduction -> head lanes)
+static void tile_rows(const WtHost &W, const WtDesc &d, const std::vector<double> &x, bool wfirst, std::vector<double> &rowsum,
                       std::vector<double> &xw) {
+  const int KP = W.kp, ns = d.geom & 0xff, gmax = d.geom >> 8, nslots = ns * KP;
   const unsigned char *b = W.blob.data() + (size_t)d.off16 * 16;
   const double *val = reinterpret_cast<const double *>(b);
-  const int *col = reinterpret_cast<const int *>(b + (size_t)d.kpl * 256);
-  const unsigned short *ends = reinterpret_cast<const unsigned short *>(b + (size_t)d.kpl * 384);
-  double p[32][kWtKpl];
-  unsigned e[32];
-  double tail[32], sc[32], acc[32];
-  int rb[32], cnt[32];
-  for (int l = 0; l < 32; ++l) {
-    for (int k = 0; k < kWtKpl; ++k) p[l][k] = k < d.kpl ? val[k * 32 + l] * x[col[k * 32 + l]] : 0.0;
-    e[l] = ends[l];
-    const int last = 31 - clz32(e[l]);
-    tail[l] = 0.0;
-    for (int k = 0; k < kWtKpl; ++k)
-      if (k > last) tail[l] += p[l][k];
-  }
-  unsigned has = 0;
+  const int *col = reinterpret_cast<const int *>(b + (size_t)nslots * 256);
+  const unsigned *heads = reinterpret_cast<const unsigned *>(b + (size_t)nslots * 384);
+  double p[32][kWtSlots];
   for (int l = 0; l < 32; ++l)
-    if (e[l]) has |= 1u << l;
-  int dist[32];
-  for (int l = 0; l < 32; ++l) {
-    const unsigned upto = has & (0xffffffffu >> (31 - l));
-    dist[l] = l - (upto ? 31 - clz32(upto) : 0);
-    sc[l] = tail[l];
-    cnt[l] = __builtin_popcount(e[l]);
-    rb[l] = cnt[l];
-  }
-  for (int o = 1; o < 32; o <<= 1) {
-    double t[32];
-    int ti[32];
-    for (int l = 0; l < 32; ++l) { t[l] = sc[l >= o ? l - o : l]; ti[l] = rb[l >= o ? l - o : l]; }   // shfl_up: own value when out of range
+    for (int k = 0; k < kWtSlots; ++k) p[l][k] = k < nslots ? val[k * 32 + l] * x[col[k * 32 + l]] : 0.0;
+  int rowbase = 0;
+  for (int s = 0; s < ns; ++s) {
+    const unsigned H = heads[s];
+    double acc[32], xwv[32];
+    int dist[32];
     for (int l = 0; l < 32; ++l) {
-      if (o <= dist[l]) sc[l] += t[l];
-      if (l >= o) rb[l] += ti[l];
+      const bool head = (H >> l) & 1u;
+      acc[l] = 0.0; xwv[l] = 0.0;
+      for (int j = 0; j < KP; ++j) {
+        if (j == 0 && wfirst && head) xwv[l] = p[l][s * KP];
+        else acc[l] += p[l][s * KP + j];
+      }
+      const unsigned above = l < 31 ? (H >> (l + 1)) : 0u;
+      dist[l] = above ? ffs32(above) - 1 : 31 - l;
     }
-  }
-  for (int l = 0; l < 32; ++l) { acc[l] = l == 0 ? 0.0 : sc[l - 1]; rb[l] -= cnt[l]; }
-  for (int l = 0; l < 32; ++l)
-    for (int k = 0; k < kWtKpl; ++k) {
-      const bool end = (e[l] >> k) & 1u;
-      if (wlast) {
-        if (end) { rowsum[d.r0 + rb[l]] = acc[l]; xw[d.r0 + rb[l]] = p[l][k]; ++rb[l]; acc[l] = 0.0; }
-        else acc[l] += p[l][k];
-      } else {
-        acc[l] += p[l][k];
-        if (end) { rowsum[d.r0 + rb[l]] = acc[l]; ++rb[l]; acc[l] = 0.0; }
+    for (int o = 1; o < 32; o <<= 1) {
+      if (o < gmax) {
+        double t[32];
+        for (int l = 0; l < 32; ++l) t[l] = acc[l + o < 32 ? l + o : l];   // shfl_down: own value when out of range
+        for (int l = 0; l < 32; ++l)
+          if (o <= dist[l]) acc[l] += t[l];
       }
     }
+    for (int l = 0; l < 32; ++l)
+      if ((H >> l) & 1u) {
+        const int r = rowbase + __builtin_popcount(H & ((1u << l) - 1u));
+        rowsum[d.r0 + r] = acc[l];
+        xw[d.r0 + r] = xwv[l];
+      }
+    rowbase += __builtin_popcount(H);
+  }
 }
 
 static int run_case(int m, int n, double mean_len, double p_empty, bool wlast, int n_ghost, unsigned seed) {
@@ -79,7 +70,7 @@ static int run_case(int m, int n, double mean_len, double p_empty, bool wlast, i
     int len = 0;
     if (U(rng) >= p_empty) {
       len = 1 + (int)(-std::log(1.0 - U(rng) * 0.999) * (mean_len - 1.0));
-      if (len > kWtTileNnz) len = kWtTileNnz;
+      if (len > kWtMaxRow) len = kWtMaxRow;
     }
     if (wlast && len == 0) len = 1;   // the merged A_fc|W operator always has the W entry
     for (int k = 0; k < len; ++k) { ja.push_back((int)(U(rng) * (n + n_ghost)) % (n + n_ghost)); a.push_back(U(rng) - 0.5); }
@@ -88,21 +79,22 @@ static int run_case(int m, int n, double mean_len, double p_empty, bool wlast, i
   std::vector<double> x((size_t)n + n_ghost);
   for (double &v : x) v = U(rng);
   WtHost W;
-  build_wt(m, n, ia.data(), ja.data(), a.data(), &W);
+  build_wt(m, n, ia.data(), ja.data(), a.data(), wlast, &W);
   if (!W.ok) { printf("FAIL: builder refused a matrix without long rows\n"); return 1; }
   std::vector<double> rs((size_t)m, 1e300), xw((size_t)m, 1e300);
   std::vector<int> covered((size_t)m, 0);
   size_t bytes = 0;
   for (size_t t = 0; t < W.desc.size(); ++t) {
     const WtDesc &d = W.desc[t];
-    if (d.kpl < 1 || d.kpl > kWtKpl || d.nrows < 1 || d.nrows > 32 * W.rq) { printf("FAIL: tile %zu geometry kpl %d rows %d\n", t, d.kpl, d.nrows); return 1; }
+    const int ns = d.geom & 0xff;
+    if (ns < 1 || ns * W.kp > kWtSlots || d.nrows < 1 || d.nrows > 32 * ns) { printf("FAIL: tile %zu geometry ns %d kp %d rows %d\n", t, ns, W.kp, d.nrows); return 1; }
     for (int r = 0; r < d.nrows; ++r) covered[d.r0 + r]++;
     // interior tiles first
     bool ghost = false;
     for (int r = d.r0; r < d.r0 + d.nrows; ++r)
       for (int q = ia[r]; q < ia[r + 1]; ++q) ghost |= ja[q] >= n;
     if (ghost != ((int)t >= W.n_int)) { printf("FAIL: tile %zu interior/boundary order\n", t); return 1; }
-    bytes += (size_t)d.kpl * 384 + 64;
+    bytes += (size_t)ns * W.kp * 384 + 32;
     tile_rows(W, d, x, wlast, rs, xw);
   }
   if (bytes + 16 != W.blob.size()) { printf("FAIL: blob size %zu vs tiles %zu\n", W.blob.size(), bytes); return 1; }
@@ -134,10 +126,10 @@ int main() {
   bad += run_case(257, 64, 256.0, 0.0, false, 0, 7); ++n;     // rows of (up to) a whole tile
   // a row longer than a tile must be refused (the operator then stays on the CSR stream kernel)
   {
-    std::vector<int> ia = {0, kWtTileNnz + 1}, ja((size_t)kWtTileNnz + 1, 0);
-    std::vector<double> a((size_t)kWtTileNnz + 1, 1.0);
+    std::vector<int> ia = {0, kWtMaxRow + 1}, ja((size_t)kWtMaxRow + 1, 0);
+    std::vector<double> a((size_t)kWtMaxRow + 1, 1.0);
     WtHost W;
-    build_wt(1, 1, ia.data(), ja.data(), a.data(), &W);
+    build_wt(1, 1, ia.data(), ja.data(), a.data(), false, &W);
     if (W.ok) { printf("FAIL: long row accepted\n"); ++bad; }
     ++n;
   }

@@ -96,3 +96,19 @@ def vcycle(H, b):
                     xc = xc + inv_apply(lv.inv_A_cc, lv.A_cc, rhs - lv.A_cc @ xc)
                 x[C] = xc
     return x
+
+
+def vcycle_full(H, b):
+    """-pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1) with inv_A_ff(l) ~ A_l^-1 on all unknowns,
+    residual restriction R (b - A x), x += P e (src/AIR_MG_Setup.F90:978-1074)."""
+    As = [lv.A for lv in H.levels]
+
+    def rec(l, bl):
+        if l == len(H.levels):
+            return inv_apply(H.inv_coarse, H.coarse_matrix, bl)
+        lv = H.levels[l]
+        x = inv_apply(lv.inv_A_ff, As[l], bl)
+        e = rec(l + 1, lv.R @ (bl - As[l] @ x))
+        x = x + lv.P @ e
+        return x + inv_apply(lv.inv_A_ff, As[l], bl - As[l] @ x)
+    return rec(0, np.asarray(b, dtype=np.float64))
