@@ -47,7 +47,7 @@ def _get_inv(d, key):
 
 
 def to_dict(H, with_A=True):
-    d = {"no_levels": np.asarray(H.no_levels)}
+    d = {"no_levels": np.asarray(H.no_levels), "full_smoothing": np.asarray(int(bool(H.options.full_smoothing_up_and_down)))}
     if with_A:
         _put_csr(d, "A", H.A)
     for l, lv in enumerate(H.levels):
@@ -60,6 +60,8 @@ def to_dict(H, with_A=True):
         for name in ("A_ff", "A_fc", "R", "P"):
             _put_csr(d, k + "_" + name, getattr(lv, name))
         _put_inv(d, k + "_inv_A_ff", lv.inv_A_ff)
+        if lv.A is not None:
+            _put_csr(d, k + "_A", lv.A)
         if lv.A_cf is not None and lv.A_cc is not None:
             _put_csr(d, k + "_A_cf", lv.A_cf)
             _put_csr(d, k + "_A_cc", lv.A_cc)
@@ -78,6 +80,8 @@ def from_dict(d):
                    A_ff=_get_csr(d, k + "_A_ff"), A_fc=_get_csr(d, k + "_A_fc"), inv_A_ff=_get_inv(d, k + "_inv_A_ff"),
                    R=_get_csr(d, k + "_R"), P=_get_csr(d, k + "_P"), smooth_order=[int(v) for v in d[k + "_smooth"]],
                    aff_diag=bool(int(d[k + "_affdiag"])))
+        if (k + "_A_indptr") in d:
+            lv.A = _get_csr(d, k + "_A")
         if (k + "_A_cc_indptr") in d:
             lv.A_cf = _get_csr(d, k + "_A_cf")
             lv.A_cc = _get_csr(d, k + "_A_cc")
@@ -85,7 +89,9 @@ def from_dict(d):
         levels.append(lv)
     cm = _get_csr(d, "coarse_matrix")
     A = _get_csr(d, "A") if "A_indptr" in d else (None if levels else cm)
-    return Hierarchy(A=A, levels=levels, coarse_matrix=cm, inv_coarse=_get_inv(d, "inv_coarse"), options=AirOptions())
+    full = bool(int(d["full_smoothing"])) if "full_smoothing" in d else False
+    return Hierarchy(A=A, levels=levels, coarse_matrix=cm, inv_coarse=_get_inv(d, "inv_coarse"),
+                     options=AirOptions(full_smoothing_up_and_down=full))
 
 
 def save(path, H, compressed=True, **extra):

@@ -57,6 +57,7 @@ class LocalHierarchy:
         self.levels = []      # dicts: n, rstart, is_fine, is_coarse, smooth, ops{which: LocalOperator}, inv_ff, inv_cc
         self.rangesV = []     # per level: global ownership offsets (nranks + 1)
         self.rangesF = []
+        self.full_smoothing = False   # -pc_air_full_smoothing_up_and_down
 
     def local_rows(self):
         return self.levels[0]["n"]
@@ -65,6 +66,8 @@ class LocalHierarchy:
         return [int(r[-1]) for r in self.rangesV]
 
     def feed(self, sink):
+        if self.full_smoothing:
+            sink.set_option("full_smoothing_up_and_down", 1)
         for l, lv in enumerate(self.levels, start=1):
             sink.set_level(l, lv["n"], lv["is_fine"], lv["is_coarse"], lv["smooth"], rstart=lv["rstart"])
             for which, op in lv["ops"].items():
@@ -88,6 +91,9 @@ def partition(H, nranks, only=None):
     materialised (the other entries carry the ownership ranges only)."""
     NL = H.no_levels
     out = [LocalHierarchy(r, nranks, NL) for r in range(nranks)]
+    full = bool(getattr(H.options, "full_smoothing_up_and_down", False))
+    for lh in out:
+        lh.full_smoothing = full
     todo = range(nranks) if only is None else [only]
     rv = split_ownership(H.levels[0].n if H.levels else H.coarse_matrix.shape[0], nranks)
 
@@ -114,15 +120,20 @@ def partition(H, nranks, only=None):
             def put(which, mat, rrange, crange):
                 dd, oo, gg = _split_cols(mat[rrange[r]:rrange[r + 1]], crange[r], crange[r + 1])
                 d["ops"][which] = LocalOperator(dd, oo, gg, crange[r])
-            put(AFF, lv.A_ff, rf, rf)
-            put(AFC, lv.A_fc, rf, rc)
             put(R, lv.R, rc, rv)
             put(P, lv.P, rv, rc)
-            if lv.A_cf is not None and lv.A_cc is not None:
-                put(ACF, lv.A_cf, rc, rf)
-                put(ACC, lv.A_cc, rc, rc)
-                d["inv_cc"] = local_inv(lv.inv_A_cc, rc, rc, r)
-            d["inv_ff"] = local_inv(lv.inv_A_ff, rf, rf, r)
+            if full:
+                # the smoother acts on all unknowns of the level: coarse_matrix(level) and its approximate inverse
+                put(COARSE, lv.A, rv, rv)
+                d["inv_ff"] = local_inv(lv.inv_A_ff, rv, rv, r)
+            else:
+                put(AFF, lv.A_ff, rf, rf)
+                put(AFC, lv.A_fc, rf, rc)
+                if lv.A_cf is not None and lv.A_cc is not None:
+                    put(ACF, lv.A_cf, rc, rf)
+                    put(ACC, lv.A_cc, rc, rc)
+                    d["inv_cc"] = local_inv(lv.inv_A_cc, rc, rc, r)
+                d["inv_ff"] = local_inv(lv.inv_A_ff, rf, rf, r)
             out[r].levels.append(d)
             out[r].rangesV.append(rv.copy())
             out[r].rangesF.append(rf.copy())

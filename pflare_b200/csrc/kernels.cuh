@@ -338,11 +338,12 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 // its own mbarrier.  Per tile the warp runs two software-pipelined stages:
 //   A (one tile ahead)  read the tile's column indices from shared memory and issue the x gathers
 //                       and the loads of the rows' epilogue operands into registers;
-//   B                   products in registers; per sub-tile every lane sums its KP slots and a
-//                       segmented shuffle reduction over the lanes of a row leaves the row sum in
-//                       the row's head lane; row sums go to shared memory (the consumed value area
-//                       of the stage) so that the epilogue runs with one row per lane (coalesced
-//                       vector traffic), 8 / KP rows per lane.
+//   B                   products into registers, after which the ring slot is refilled at once (the next
+//                       bulk copy overlaps the rest of the tile's work); per sub-tile every lane sums
+//                       its KP slots (pairwise) and a segmented shuffle reduction over the lanes of a
+//                       row leaves the row sum in the row's head lane; row sums go through a small
+//                       shared-memory buffer so that the epilogue runs with one row per lane
+//                       (coalesced vector traffic), 8 / KP rows per lane.
 // No __syncthreads: a warp never waits for another warp, so one warp's gather latency is hidden by
 // the other warps of the SM and the bulk stream never drains.
 template <int EPI, int KP, bool GHOST, int NW, int STAGES>
@@ -353,14 +354,16 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
   constexpr int NSLOT = kWtSlots;
   constexpr int NS = kWtSlots / KP;            // sub-tiles per tile == rows per lane in the epilogue
   constexpr bool AHEAD = E::kPre * NS <= 16;   // epilogue operands prefetched one tile ahead (else at the start of stage B)
+  constexpr int RS_BYTES = NS * 32 * 8;        // row sums of the tile being reduced (the ring slot itself is refilled early)
   constexpr int XW_BYTES = XW ? NS * 32 * 8 : 0;
-  constexpr int WARP_BYTES = STAGES * kWtStageBytes + XW_BYTES;
+  constexpr int WARP_BYTES = STAGES * kWtStageBytes + RS_BYTES + XW_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[NW][STAGES];
   __shared__ WtDesc sdesc[NW][STAGES];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned char *wbase = smem_raw + (size_t)w * WARP_BYTES;
-  double *xw_s = reinterpret_cast<double *>(wbase + STAGES * kWtStageBytes);
+  double *rs_s = reinterpret_cast<double *>(wbase + STAGES * kWtStageBytes);
+  double *xw_s = rs_s + NS * 32;
   const int nwarps = gridDim.x * NW;
   const int first = blockIdx.x * NW + w;
   const int my = first < op.nwt ? (op.nwt - first + nwarps - 1) / nwarps : 0;
@@ -428,25 +431,30 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
     for (int k = 0; k < NSLOT; ++k) p[k] = xn[k];
 #pragma unroll
     for (int q = 0; q < NS; ++q) pc[q] = pn[q];
-    if (it + 1 < my) stage_a(it + 1);
-    // ---- stage B
+    // ---- stage B, part 1: products and head masks into registers -> the ring slot is consumed
     const int slot = it % STAGES;
     unsigned char *st = wbase + slot * kWtStageBytes;
-    double *val_s = reinterpret_cast<double *>(st);
+    const double *val_s = reinterpret_cast<const double *>(st);
     const int ns = d.geom & 0xff, gmax = d.geom >> 8;
     const int nslots = ns * KP;
-    if (!AHEAD) {
-#pragma unroll
-      for (int q = 0; q < NS; ++q)
-        if (lane + 32 * q < d.nrows) pc[q] = E::prefetch(op, d.r0 + lane + 32 * q);
-    }
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) p[k] = (k < nslots) ? val_s[k * 32 + lane] * p[k] : 0.0;
     const unsigned *heads = reinterpret_cast<const unsigned *>(st + nslots * 384);
     unsigned hd[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) hd[s] = (s < ns) ? heads[s] : 0u;
-    __syncwarp();   // every lane holds its values: the value area now receives the row sums
+    // refill the slot NOW (not at the end of the iteration): the bulk copy of tile it + STAGES then has the
+    // whole reduction / epilogue of this tile and stage A of the next one to land
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my generic-proxy reads of the slot before the next bulk copy into it
+    __syncwarp();
+    if (lane == 0 && it + STAGES < my) issue(it + STAGES);
+    if (it + 1 < my) stage_a(it + 1);
+    if (!AHEAD) {
+#pragma unroll
+      for (int q = 0; q < NS; ++q)
+        if (lane + 32 * q < d.nrows) pc[q] = E::prefetch(op, d.r0 + lane + 32 * q);
+    }
+    // ---- stage B, part 2: row sums
     const bool wf = (EPI == EPI_AFCW || EPI == EPI_AFCW_LOCAL) || (EPI == EPI_GENERIC && op.wlast);
     int rowbase = 0;
 #pragma unroll
@@ -454,29 +462,30 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
       if (s < ns) {
         const unsigned H = hd[s];
         const bool head = (H >> lane) & 1u;
-        double acc = 0.0, xw = 0.0;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) {
-          if (XW && j == 0) {
-            if (wf && head) xw = p[s * KP];   // merged A_fc|W: the row's first entry is the W entry
-            else acc += p[s * KP];
-          } else {
-            acc += p[s * KP + j];
-          }
-        }
+        double xw = 0.0;
+        double q0 = p[s * KP];
+        if (XW && wf && head) { xw = q0; q0 = 0.0; }   // merged A_fc|W: the row's first entry is the W entry
+        double acc;
+        if (KP == 1) acc = q0;
+        else if (KP == 2) acc = q0 + p[s * KP + (KP > 1 ? 1 : 0)];
+        else if (KP == 4) acc = (q0 + p[s * KP + (KP > 1 ? 1 : 0)]) + (p[s * KP + (KP > 2 ? 2 : 0)] + p[s * KP + (KP > 2 ? 3 : 0)]);
+        else acc = ((q0 + p[(KP > 1 ? 1 : 0)]) + (p[(KP > 2 ? 2 : 0)] + p[(KP > 2 ? 3 : 0)])) +
+                   ((p[(KP > 4 ? 4 : 0)] + p[(KP > 4 ? 5 : 0)]) + (p[(KP > 4 ? 6 : 0)] + p[(KP > 4 ? 7 : 0)]));
         // segmented reduction over the lanes of a row (toward its head lane)
-        const unsigned above = lane < 31 ? (H >> (lane + 1)) : 0u;
-        const int dist = above ? __ffs((int)above) - 1 : 31 - lane;   // lanes of my row after me
+        if (gmax > 1) {
+          const unsigned above = lane < 31 ? (H >> (lane + 1)) : 0u;
+          const int dist = above ? __ffs((int)above) - 1 : 31 - lane;   // lanes of my row after me
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          if (o < gmax) {
-            const double t = __shfl_down_sync(0xffffffffu, acc, o);
-            if (o <= dist) acc += t;
+          for (int o = 1; o < 32; o <<= 1) {
+            if (o < gmax) {
+              const double t = __shfl_down_sync(0xffffffffu, acc, o);
+              if (o <= dist) acc += t;
+            }
           }
         }
         if (head) {
           const int r = rowbase + __popc(H & ((1u << lane) - 1u));
-          val_s[r] = acc;
+          rs_s[r] = acc;
           if (XW && wf) xw_s[r] = xw;
         }
         rowbase += __popc(H);
@@ -486,12 +495,9 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
       const int r = lane + 32 * q;
-      if (r < d.nrows) E::finish(op, d.r0 + r, val_s[r], (XW && wf) ? xw_s[r] : 0.0, pc[q]);
+      if (r < d.nrows) E::finish(op, d.r0 + r, rs_s[r], (XW && wf) ? xw_s[r] : 0.0, pc[q]);
     }
-    // generic-proxy accesses to this slot are done; order them before the next bulk copy into it
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0 && it + STAGES < my) issue(it + STAGES);
+    __syncwarp();   // the row-sum buffer is reused by the next tile
   }
 }
 
@@ -631,28 +637,39 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(const EwOp e) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += gridDim.x * blockDim.x) ew_apply(e, i);
 }
 
-// Dense collapsed tail: y = T x, T row-major n x n.  One warp per row, fixed summation order
-// (8 interleaved partial sums per lane, then a shuffle tree) -> deterministic.
+// Dense collapsed tail: y = T x, T row-major n x n.  One CTA per row (grid-stride): every warp streams a
+// contiguous eighth of the row with 8 independent loads per lane in flight, fixed summation order
+// (8 interleaved partial sums per lane, a shuffle tree, then the warps in order) -> deterministic.
 __global__ void __launch_bounds__(kThreads) dense_gemv_kernel(int n, const double *__restrict__ T, const double *__restrict__ x,
                                                               double *__restrict__ y) {
   pdl_launch_dependents();
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int row = warp; row < n; row += nwarps) {
+  __shared__ double part[kThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int NWARP = kThreads / 32;
+  const int chunk = (n + NWARP - 1) / NWARP;
+  const int j0 = w * chunk, j1 = min(n, j0 + chunk);
+  for (int row = blockIdx.x; row < n; row += gridDim.x) {
     const double *t = T + (size_t)row * n;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int j = lane;
-    for (; j + 7 * 32 < n; j += 8 * 32) {
+    int j = j0 + lane;
+    for (; j + 7 * 32 < j1; j += 8 * 32) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) acc[u] += __ldcs(t + j + u * 32) * x[j + u * 32];
     }
-    for (int u = 0; j < n; j += 32, ++u) acc[u] += __ldcs(t + j) * x[j];
+    for (int u = 0; j < j1; j += 32, ++u) acc[u] += __ldcs(t + j) * x[j];
     double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) y[row] = s;
+    if (lane == 0) part[w] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0.0;
+#pragma unroll
+      for (int k = 0; k < NWARP; ++k) r += part[k];
+      y[row] = r;
+    }
+    __syncthreads();
   }
 }
 

@@ -146,6 +146,7 @@ struct Level {
   Inv inv_ff, inv_cc;
   // device
   DevCSR Z, W, Afc, Afcw, Aff, Acf, Acc, Coarse;   // Afcw = A_fc with the one-point W entry appended to every row
+  DevCSR Znat;                 // level 1 with the fused entry permutation: Z with NATURAL column indices (gathers from the caller's b)
   DevCSR Pn;                   // full smoothing: P = [W; I] in nested ordering (x_l += P x_{l+1}); Coarse = A_l on every level
   bool w_onepoint = false;
   bool aff_diag_only = false;
@@ -163,7 +164,13 @@ struct Level {
 enum { OPK_SPMV = 0, OPK_EW = 1, OPK_XCHG = 2, OPK_GATHER0 = 3, OPK_SCATTER0 = 4, OPK_CHILD = 5, OPK_DENSE = 6, OPK_EPOCH = 7, OPK_ACK = 8, OPK_XWAIT = 9 };
 const int kMaxInst = 4096;   // exchange instances per cycle the flag block has room for
 
+// Placeholders for the caller's vectors inside the cycle program (entry / exit permutation fused into the level-1
+// ops): patched with the real pointers of each apply; the ops that carry them run outside the CUDA graph.
+double *const kUserB = reinterpret_cast<double *>((uintptr_t)8);
+double *const kUserX = reinterpret_cast<double *>((uintptr_t)16);
+
 struct Op {
+  bool user = false;            // references kUserB / kUserX
   int kind = OPK_SPMV;
   SpmvOp s{};
   EwOp e{};
@@ -206,6 +213,9 @@ struct Ctx {
   // options
   int use_graph = 1, fuse = 1;
   int fuse_epi = 1;      // compile-time specialised epilogue classes (0: every op runs the generic epilogue)
+  int fuse_perm = 1;     // natural <-> nested permutation of b / x fused into the level-1 ops (serial Kaskade contexts)
+  bool io_fused = false; // decided at finalize_setup
+  int n_head = 0, tail_begin = -1;   // program ops [0, n_head) and [tail_begin, end) reference the caller's vectors: launched per apply, outside the graph
   int full_smooth = 0;   // -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1), inv_A_ff(l) ~ A_l^-1 on all unknowns
   int dense_rows = 4096; // levels with <= this many rows are collapsed into one dense matrix (0 = off)
   int kernel = 2;        // 0: smem-staged stream kernel, 1: round-1 TMA kernel (CTA tiles), 2: warp-tile kernel
@@ -313,7 +323,10 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int s
   } else if (h.n_ghost > 0) {
     return fail(2, "operator has ghost columns but the context has a single rank");
   }
-  if (c->device < 0) return 0;  // host-only planning context
+  if (c->device < 0) {  // host-only planning context (the warp-tile layout is still built when asked for: CPU-side checks)
+    if (getenv("PFLARE_B200_PLAN_BUILDS_TILES") && c->kernel == 2) { WtHost W; build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), wfirst, &W); }
+    return 0;
+  }
   int rc;
   d->wt = false;
   if (c->kernel == 2) {
@@ -431,6 +444,7 @@ struct Builder {
   std::vector<Op> *out;
   int level = 0;
   bool use_p2p = false;   // only the cycle program owns exchange instances; ad-hoc op lists go through NCCL / copies
+  bool io = false;        // cycle program of a context with fused entry / exit permutation: level-1 ops read b / write x in natural order
 
   SpmvOp base(const DevCSR &A, const double *x) {
     SpmvOp s{};
@@ -642,17 +656,22 @@ struct Builder {
       const DevCSR &A = fuse_w ? Lv.Afcw : Lv.Afc;
       SpmvOp s = base(A, xc);
       s.aux = bf; s.alpha = 1.0; s.beta = -1.0;
+      const bool io1 = io && level == 1;
+      if (io1) { s.aux = kUserB; s.aux_idx = Lv.d_inv; }   // b_f read straight from the caller's b (natural ordering)
       double extra = 0;
       if (fuse_w) { s.wlast = 1; s.wout = xf; extra += 8.0 * Lv.nf; }
       if (local) {
         s.fd_a = Lv.aff_diag; s.fd_m = Lv.inv_ff.ddiag; s.fd_its = its;
         extra += 16.0 * Lv.nf;
+        if (io1) { s.wout_idx = Lv.d_inv; s.xnat = kUserX; }   // x_f written straight into the caller's x
         push_spmv(s, A, 7, 1, 0, extra);
         out->back().nnz += 2.0 * its * Lv.nf;   // the its x (diagonal A_ff + diagonal M_ff) products folded into this op
+        out->back().user = io1;
         return 0;
       }
       s.out = S[0]; s.out_mode = 1;
       push_spmv(s, A, 3, 1, 1, extra);
+      out->back().user = io1;
     }
     for (int f = 0; f < its; ++f) {
       SpmvOp s = base(Lv.Aff, xf);  // r = rhs - A_ff x_f     (src/FC_Smooth.F90:544-549)
@@ -661,6 +680,17 @@ struct Builder {
       push_spmv(s, Lv.Aff, 4, 1, 1);
       int rc = emit_inv(Lv.inv_ff, Lv.Aff, Lv.aff_diag, Lv.nf, S[1], xf, 2);  // x_f += M_ff r  (:552-557)
       if (rc) return rc;
+    }
+    if (io && level == 1) {
+      // exit permutation of the F points: folded into the last update of x_f when that is `x_f += M r` with an
+      // assembled M, otherwise one scatter over the F points
+      Op &last = out->back();
+      if (last.kind == OPK_SPMV && last.s.epi == EPI_ADD && last.s.out == xf) {
+        last.s.wout_idx = Lv.d_inv; last.s.xnat = kUserX; last.user = true;
+      } else {
+        push_ew(Lv.nf, xf, nullptr, nullptr, 1.0, kUserX, 1, nullptr, Lv.d_inv);
+        out->back().user = true;
+      }
     }
     return 0;
   }
@@ -851,7 +881,7 @@ int launch_r1(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
 template <int EPI, int KP, bool GH, int ST>
 int launch_wt_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   auto kern = spmv_wt_kernel<EPI, KP, GH, kWtWarps, ST>;
-  const size_t smem = (size_t)kWtWarps * (ST * kWtStageBytes + (EpiT<EPI>::kXw ? (kWtSlots / KP) * 32 * 8 : 0));
+  const size_t smem = (size_t)kWtWarps * (ST * kWtStageBytes + (kWtSlots / KP) * 32 * 8 * (EpiT<EPI>::kXw ? 2 : 1));
   static int per_sm = 0;
   int rc = kernel_per_sm(kern, kWtWarps * 32, smem, &per_sm);
   if (rc || dry) return rc;
@@ -926,7 +956,7 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
   } else if (o.kind == OPK_DENSE) {
     if (dry) return 0;
     const int n = c->dense_n;
-    int grid = std::min((n * 32 + kThreads - 1) / kThreads, c->num_sms * 8);
+    int grid = std::min(n, c->num_sms * 8);   // one CTA per row
     CUDA_TRY(launch_k(c->pdl != 0, dense_gemv_kernel, grid, kThreads, 0, st, n, (const double *)c->dense_T, (const double *)o.e.a, o.e.out));
   } else {
     if (dry) return 0;
@@ -1522,7 +1552,7 @@ void release_device_state(Ctx *c) {
   c->child_b = c->child_x = nullptr;
   c->arena = nullptr; c->arena_bytes = 0; c->p2p_ready = false; c->d_peer_flags = nullptr; c->d_done = nullptr;
   for (Level &Lv : c->L) {
-    for (DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.Pn, &Lv.inv_ff.d, &Lv.inv_cc.d}) *A = DevCSR();
+    for (DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.Pn, &Lv.Znat, &Lv.inv_ff.d, &Lv.inv_cc.d}) *A = DevCSR();
     Lv.inv_ff.ddiag = Lv.inv_cc.ddiag = nullptr;
     Lv.aff_diag = Lv.acc_diag = Lv.coarse_diag = Lv.bc_save = nullptr;
     Lv.d_pos = Lv.d_inv = nullptr;
@@ -2363,6 +2393,10 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   if (k == "graph") c->use_graph = value != 0;
   else if (k == "fuse") c->fuse = value != 0;
   else if (k == "epi_classes") c->fuse_epi = value != 0;
+  else if (k == "fuse_perm") {
+    if (c->finalized || c->planned) return fail(2, "fuse_perm must be set before finalize_setup");
+    c->fuse_perm = value != 0;
+  }
   else if (k == "full_smoothing_up_and_down") {
     if (c->finalized || c->planned) return fail(2, "full_smoothing_up_and_down must be set before finalize_setup");
     c->full_smooth = value != 0;

@@ -60,7 +60,15 @@ CASES = {
     # DG upwind surrogate (configs[2]), matrix-free smoothing
     "dg_mf": lambda: (hiergen.dg_upwind_surrogate(24, 24, 3), O(matrix_free_polys=True)),
     "dg_assembled": lambda: (hiergen.dg_upwind_surrogate(16, 16, 4), O()),
+    # -pc_air_full_smoothing_up_and_down (src/AIR_MG_Setup.F90:978-1074): PCMG multiplicative V(1,1), residual restriction
+    # R (b - A x), the smoother inverts the whole level matrix; assembled, matrix-free Horner / Newton, Jacobi
+    "fd2d_full": lambda: (hiergen.adv_diff_fd(40, 40, alpha=0.5), O(full_smoothing_up_and_down=True)),
+    "fd2d_full_mf": lambda: (hiergen.adv_diff_fd(40, 40, alpha=0.5), O(full_smoothing_up_and_down=True, matrix_free_polys=True)),
+    "fd2d_full_mf_newton": lambda: (_adv2(40), O(full_smoothing_up_and_down=True, matrix_free_polys=True, inverse_type=poly.NEWTON)),
+    "fd2d_full_jacobi": lambda: (hiergen.adv_diff_fd(32, 32, alpha=1.0), O(full_smoothing_up_and_down=True, inverse_type=poly.JACOBI)),
 }
+
+FULL_CASES = ["fd2d_full", "fd2d_full_mf", "fd2d_full_mf_newton", "fd2d_full_jacobi"]
 
 # cases small enough for the CPU-only suite and the golden fixtures
 GOLDEN = ["adv1d_makefile", "fd2d_25", "fd3d_10_lump", "fd2d_mf_newton", "fd2d_fcf", "dg_mf"]

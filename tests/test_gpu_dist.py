@@ -43,7 +43,8 @@ def _cluster_apply(H, nranks, b, **opts):
 
 @pytest.mark.parametrize("nranks", [2, 3, 4])
 @pytest.mark.parametrize("name", ["fd2d_64", "fd2d_mf_newton", "fd2d_fcf", "fd2d_idealW", "fd3d_10_lump", "dg_mf",
-                                  "fd2d_diagAff", "fd2d_trunc_newton", "adv1d_makefile", "fd2d_ffcc_mf", "fd2d_mf_neumann"])
+                                  "fd2d_diagAff", "fd2d_trunc_newton", "adv1d_makefile", "fd2d_ffcc_mf", "fd2d_mf_neumann",
+                                  "fd2d_full", "fd2d_full_mf_newton"])
 def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
     A, H = cases.build(name)
     b = cases.rhs(A.shape[0])
@@ -59,7 +60,7 @@ def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
 
 
 @pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=1), dict(dense_rows=0), dict(pdl=0), dict(p2p=1), dict(p2p=1, graph=0), dict(overlap=0), dict(overlap=0, graph=0),
-                                  dict(epi_classes=0), dict(wt_stages=4, p2p=1), dict(max_ctas=1), dict(kernel=1, p2p=1)], ids=str)
+                                  dict(epi_classes=0), dict(wt_stages=3, p2p=1), dict(max_ctas=1), dict(kernel=1, p2p=1)], ids=str)
 def test_partitioned_execution_modes(built_libs, opts):
     A, H = cases.build("fd2d_64")
     b = cases.rhs(A.shape[0], seed=3)

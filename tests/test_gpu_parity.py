@@ -56,8 +56,8 @@ def test_vcycle_parity(built_libs, name, dense_rows):
                                   dict(kernel=1, ctas_per_sm=1),
                                   # warp-tile kernel: ring depth, generic (run-time branched) epilogue instead of the compiled classes,
                                   # ONE persistent CTA per SM / in total (many tiles per warp: the mbarrier ring wraps many times)
-                                  dict(wt_stages=4, dense_rows=0), dict(epi_classes=0, dense_rows=0), dict(epi_classes=0, fuse=0, dense_rows=0),
-                                  dict(ctas_per_sm=1, dense_rows=0), dict(max_ctas=1, dense_rows=0), dict(max_ctas=1, wt_stages=4, dense_rows=0, graph=0, pdl=0),
+                                  dict(wt_stages=3, dense_rows=0), dict(epi_classes=0, dense_rows=0), dict(epi_classes=0, fuse=0, dense_rows=0),
+                                  dict(ctas_per_sm=1, dense_rows=0), dict(max_ctas=1, dense_rows=0), dict(max_ctas=1, wt_stages=3, dense_rows=0, graph=0, pdl=0),
                                   dict(kernel=1, max_ctas=2, dense_rows=0),
                                   # coarse levels collapsed into one dense operator (built from the same kernels at setup)
                                   dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, graph=0)],

@@ -1,7 +1,7 @@
 #!/bin/bash
 # row-aligned warp-tile format: parity + 4096^2 bench (stages 2 vs 3) + per-op table + launch list
 cd "$(dirname "$0")/../.." ; mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/r3_pytest_parity.log 2>&1; rc=$?; echo "pytest parity rc=$rc"; tail -5 gpurun_out/r3_pytest_parity.log
+timeout 900 python -X faulthandler -m pytest tests/test_gpu_parity.py -x -q -m gpu --timeout 120 > gpurun_out/r3_pytest_parity.log 2>&1; rc=$?; echo "pytest parity rc=$rc"; tail -5 gpurun_out/r3_pytest_parity.log
 [ $rc -ne 0 ] && exit 1
 B="python bench.py --size 4096 --steps 30 --warmup 5 --no-cpu-baseline"
 timeout 1200 $B --dump-ops gpurun_out/r3_ops_4096.csv --compare-opt wt_stages=3 --compare-opt wt_stages=2,pdl=0 \
