@@ -154,7 +154,10 @@ __device__ __forceinline__ void epi_finish(const SpmvOp &op, int i, double s, do
     if (op.wout_idx) op.xnat[op.wout_idx[i]] = xw;
   }
   if (op.out_mode == 1) op.out[i] = v;
-  else if (op.out_mode == 2) op.out[i] = p.out + v;
+  else if (op.out_mode == 2) {
+    op.out[i] = p.out + v;
+    if (op.wout_idx && !op.wout) op.xnat[op.wout_idx[i]] = p.out + v;
+  }
   if (op.out2) op.out2[i] = op.delta * v;
   if (op.acc_mode) {
     const double t = op.gamma * (op.acc_src ? p.accsrc : v);
@@ -179,7 +182,11 @@ template <> struct EpiT<EPI_ADD> {
   static constexpr int kPre = 1; static constexpr bool kXw = false;
   struct Pre { double o; };
   static __device__ __forceinline__ Pre prefetch(const SpmvOp &op, int i) { Pre p; p.o = op.out[i]; return p; }
-  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double, const Pre &p) { op.out[i] = p.o + s; }
+  static __device__ __forceinline__ void finish(const SpmvOp &op, int i, double s, double, const Pre &p) {
+    const double v = p.o + s;
+    if (op.wout_idx) op.xnat[op.wout_idx[i]] = v;   // last update of the level-1 F points: straight into the caller's x
+    else op.out[i] = v;
+  }
 };
 template <> struct EpiT<EPI_SET> {
   static constexpr int kPre = 0; static constexpr bool kXw = false;
@@ -216,8 +223,8 @@ template <> struct EpiT<EPI_AFCW_LOCAL> {
     double v = op.beta * s;
     v = op.alpha * p.a + v;
     for (int it = 0; it < op.fd_its; ++it) xw = xw + p.fm * (v - p.fa * xw);
-    op.wout[i] = xw;
-    if (op.wout_idx) op.xnat[op.wout_idx[i]] = xw;
+    if (op.wout_idx) op.xnat[op.wout_idx[i]] = xw;   // level 1: straight into the caller's x (natural ordering)
+    else op.wout[i] = xw;
   }
 };
 template <> struct EpiT<EPI_AXPBY_ACC> {
@@ -499,6 +506,117 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
     }
     __syncwarp();   // the row-sum buffer is reused by the next tile
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct (register-staged) engine on the same warp-tile storage: no shared memory, no barrier of any
+// kind.  The lane-interleaved blob makes the tile's column / value loads perfectly coalesced
+// (32 lanes x 4 / 8 bytes per slot, streaming cache policy), so a warp simply loads its slots, gathers
+// x, multiplies and reduces; the head lane of every row runs the row epilogue (consecutive rows ->
+// consecutive head lanes -> the vector accesses still fill whole sectors).  With no shared-memory
+// ring and ~80 registers, 24 warps per SM are resident (the TMA-ring engine: 16) and the whole L1
+// serves the gathers: latency is hidden by occupancy instead of by a software pipeline.
+__device__ __forceinline__ int ld_stream_nc(const int *p) { return __ldcs(p); }
+template <int EPI, int KP, bool GHOST>
+__global__ void __launch_bounds__(256, 3) spmv_sv_kernel(const SpmvOp op) {
+  typedef EpiT<EPI> E;
+  typedef typename E::Pre Pre;
+  constexpr bool XW = E::kXw;
+  constexpr int NSLOT = kWtSlots;
+  constexpr int NS = kWtSlots / KP;
+  constexpr bool AHEAD = E::kPre * NS <= 8;   // epilogue operands loaded before the gathers (else right before the row is finished)
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const WtDesc *__restrict__ wdesc = op.wdesc;
+  const double *__restrict__ xv = op.x;
+  const double *__restrict__ xg = op.xg;
+  const int nloc = op.nloc;
+  const bool wf = (EPI == EPI_AFCW || EPI == EPI_AFCW_LOCAL) || (EPI == EPI_GENERIC && op.wlast);
+  pdl_launch_dependents();
+  int t = gw;
+  WtDesc dn = {0u, 0, 0, 0};
+  if (t < op.nwt) dn = wdesc[t];
+  bool waited = false;
+  for (; t < op.nwt; t += nwarps) {
+    const WtDesc d = dn;
+    if (t + nwarps < op.nwt) dn = wdesc[t + nwarps];
+    const int ns = d.geom & 0xff, gmax = d.geom >> 8;
+    const int nslots = ns * KP;
+    const unsigned char *b = op.blob + (size_t)d.off16 * 16;
+    const double *val_g = reinterpret_cast<const double *>(b);
+    const int *col_g = reinterpret_cast<const int *>(b + nslots * 256);
+    const unsigned *heads = reinterpret_cast<const unsigned *>(b + nslots * 384);
+    // matrix stream: coalesced, read once
+    int c[NSLOT];
+    double p[NSLOT];
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) c[k] = (k < nslots) ? __ldcs(col_g + k * 32 + lane) : 0;
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) p[k] = (k < nslots) ? __ldcs(val_g + k * 32 + lane) : 0.0;
+    unsigned hd[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) hd[s] = (s < ns) ? __ldg(heads + s) : 0u;
+    if (!waited) { pdl_wait(); waited = true; }   // from here on the vectors written by the previous kernels are read
+    if (GHOST && lane == 0 && t == gw) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+    if (GHOST) __syncwarp();
+    // gathers
+    double xr[NSLOT];
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) {
+      xr[k] = 0.0;
+      if (k < nslots) {
+        if (GHOST) xr[k] = (c[k] >= nloc) ? __ldcg(xg + (c[k] - nloc)) : xv[c[k]];
+        else xr[k] = xv[c[k]];
+      }
+    }
+    // epilogue operands of the rows whose head lane I am
+    Pre pc[NS];
+    int row[NS];
+    {
+      int rowbase = d.r0;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const unsigned H = hd[s];
+        row[s] = ((H >> lane) & 1u) ? rowbase + __popc(H & ((1u << lane) - 1u)) : -1;
+        if (AHEAD && row[s] >= 0) pc[s] = E::prefetch(op, row[s]);
+        rowbase += __popc(H);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) p[k] *= xr[k];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s < ns) {
+        const unsigned H = hd[s];
+        double xw = 0.0;
+        double q0 = p[s * KP];
+        if (XW && wf && row[s] >= 0) { xw = q0; q0 = 0.0; }   // merged A_fc|W: the row's first entry is the W entry
+        double acc;
+        if (KP == 1) acc = q0;
+        else if (KP == 2) acc = q0 + p[s * KP + (KP > 1 ? 1 : 0)];
+        else if (KP == 4) acc = (q0 + p[s * KP + (KP > 1 ? 1 : 0)]) + (p[s * KP + (KP > 2 ? 2 : 0)] + p[s * KP + (KP > 2 ? 3 : 0)]);
+        else acc = ((q0 + p[(KP > 1 ? 1 : 0)]) + (p[(KP > 2 ? 2 : 0)] + p[(KP > 2 ? 3 : 0)])) +
+                   ((p[(KP > 4 ? 4 : 0)] + p[(KP > 4 ? 5 : 0)]) + (p[(KP > 4 ? 6 : 0)] + p[(KP > 4 ? 7 : 0)]));
+        if (gmax > 1) {
+          const unsigned above = lane < 31 ? (H >> (lane + 1)) : 0u;
+          const int dist = above ? __ffs((int)above) - 1 : 31 - lane;   // lanes of my row after me
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            if (o < gmax) {
+              const double tt = __shfl_down_sync(0xffffffffu, acc, o);
+              if (o <= dist) acc += tt;
+            }
+          }
+        }
+        if (row[s] >= 0) {
+          if (!AHEAD) pc[s] = E::prefetch(op, row[s]);
+          E::finish(op, row[s], acc, xw, pc[s]);
+        }
+      }
+    }
+  }
+  if (!waited) pdl_wait();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -219,6 +219,7 @@ struct Ctx {
   int full_smooth = 0;   // -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1), inv_A_ff(l) ~ A_l^-1 on all unknowns
   int dense_rows = 4096; // levels with <= this many rows are collapsed into one dense matrix (0 = off)
   int kernel = 2;        // 0: smem-staged stream kernel, 1: round-1 TMA kernel (CTA tiles), 2: warp-tile kernel
+  int engine = 1;        // kernel 2: 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel, no shared memory)
   int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
@@ -463,7 +464,7 @@ struct Builder {
       if (s.fd_its > 0) return s.out_mode == 0 ? EPI_AFCW_LOCAL : EPI_GENERIC;
       return (s.out_mode == 1 && !s.wout_idx) ? EPI_AFCW : EPI_GENERIC;
     }
-    if (s.wout || s.wout_idx) return EPI_GENERIC;
+    if (s.wout) return EPI_GENERIC;
     if (s.acc_mode) return (s.aux && !s.aux_idx && s.out_mode == 1) ? EPI_AXPBY_ACC : EPI_GENERIC;
     if (!s.aux) {
       if (s.beta != 1.0) return EPI_GENERIC;
@@ -891,9 +892,23 @@ int launch_wt_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   CUDA_TRY(launch_k(c->pdl != 0, kern, grid, kWtWarps * 32, smem, st, s));
   return 0;
 }
+// direct engine (no shared memory): one instantiation per (epilogue class, slots per lane, ghost columns)
+template <int EPI, int KP, bool GH>
+int launch_sv_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  auto kern = spmv_sv_kernel<EPI, KP, GH>;
+  static int per_sm = 0;
+  int rc = kernel_per_sm(kern, 256, 0, &per_sm);
+  if (rc || dry) return rc;
+  const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
+  int grid = std::min((s.nwt + 7) / 8, c->num_sms * want);   // persistent, 8 warps per CTA
+  if (c->max_ctas > 0) grid = std::min(grid, c->max_ctas);
+  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, 256, 0, st, s));
+  return 0;
+}
 template <int EPI, int KP>
 int launch_wt_kp(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   const bool gh = s.xg != nullptr;
+  if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true>(c, s, st, dry) : launch_sv_inst<EPI, KP, false>(c, s, st, dry);
   if (c->wt_stages == 3) return gh ? launch_wt_inst<EPI, KP, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 3>(c, s, st, dry);
   return gh ? launch_wt_inst<EPI, KP, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 2>(c, s, st, dry);
 }
@@ -983,7 +998,7 @@ int launch_ew_now(Ctx *c, int n, const double *a, double *out, const int *gather
   return launch_op(c, o, st);
 }
 
-int run_program(Ctx *c, cudaStream_t st, int *nkernels);
+int run_program(Ctx *c, cudaStream_t st, int *nkernels, int begin = 0, int end = -1, const double *ub = nullptr, double *ux = nullptr);
 
 // the agglomerated coarse levels on rank 0: natural-order vectors in, natural-order vectors out
 int run_child(Ctx *c, cudaStream_t st) {
@@ -1128,15 +1143,35 @@ int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op
   return 0;
 }
 
-int run_program(Ctx *c, cudaStream_t st, int *nkernels) {
+// the caller's vectors substituted for the placeholders of a `user` op
+Op patch_user(const Op &o, const double *ub, double *ux) {
+  Op q = o;
+  if (q.s.x == kUserB) q.s.x = ub;
+  if (q.s.aux == kUserB) q.s.aux = ub;
+  if (q.s.xnat == kUserX) q.s.xnat = ux;
+  if (q.e.a == kUserB) q.e.a = ub;
+  if (q.e.out == kUserX) q.e.out = ux;
+  return q;
+}
+
+// ops [begin, end) of the cycle program; `user` ops need the caller's vectors (ub, ux)
+int run_program(Ctx *c, cudaStream_t st, int *nkernels, int begin, int end, const double *ub, double *ux) {
   int nk = 0;
-  const int n = (int)c->prog.size();
+  const int n = end < 0 ? (int)c->prog.size() : end;
   std::vector<Ctx *> R{c};
   std::vector<const std::vector<Op> *> P{&c->prog};
-  for (int i = 0; i < n; ++i) {
+  for (int i = begin; i < n; ++i) {
     const Op &o = c->prog[i];
     if (op_is_empty(o)) continue;
-    int rc = exec_ops(R, P, i, i + 1, st);
+    int rc;
+    if (o.user) {
+      if (!ub || !ux) return fail(7, "internal: op %d needs the caller's vectors", i);
+      std::vector<Op> one{patch_user(o, ub, ux)};
+      std::vector<const std::vector<Op> *> P1{&one};
+      rc = exec_ops(R, P1, 0, 1, st);
+    } else {
+      rc = exec_ops(R, P, i, i + 1, st);
+    }
     if (rc) return rc;
     ++nk;
   }
@@ -1149,7 +1184,7 @@ int build_graph(Ctx *c) {
   if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
   CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   int nk = 0;
-  int rc = run_program(c, c->stream, &nk);
+  int rc = run_program(c, c->stream, &nk, c->n_head, c->tail_begin);
   cudaError_t e = cudaStreamEndCapture(c->stream, &c->graph);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(100 + (int)e, "graph capture failed: %s", cudaGetErrorString(e));
@@ -1167,6 +1202,8 @@ int build_program(Ctx *c) {
   const int LB = agg ? c->l_agg : NL;  // bottom level of this context's nested vectors
   Builder B{c, &c->prog};
   B.use_p2p = true;
+  B.io = c->io_fused;
+  c->n_head = 0; c->tail_begin = -1;
   c->n_inst = 0;
   for (DevPlan &D : c->plans) D.first_inst = D.last_inst = -1;
   if (c->p2p_ready) { Op e; e.kind = OPK_EPOCH; e.tag = 10; c->prog.push_back(e); }
@@ -1174,6 +1211,7 @@ int build_program(Ctx *c) {
   int ldense = NL + 1, dense_begin = -1, dense_end = -1;
   if (c->nranks == 1 && c->dense_rows > 0 && c->device >= 0) {
     for (int l = NL; l >= 1; --l) { if (c->L[l].n <= c->dense_rows) ldense = l; else break; }
+    if (c->io_fused && ldense < 2) ldense = 2;   // level 1 carries the fused entry / exit permutation
     if (ldense > NL - 1) ldense = NL + 1;   // >= 2 levels
   }
   // -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1) (src/AIR_MG_Setup.F90:978-1074), going down
@@ -1203,6 +1241,17 @@ int build_program(Ctx *c) {
     Level &Lv = c->L[l];
     B.level = l;
     if (l == ldense) dense_begin = (int)c->prog.size();
+    if (l == 1 && c->io_fused) {
+      // entry permutation fused into the level-1 restriction: b_2 = b_c + Z b_f with b read in natural ordering
+      // (Z stored with natural column indices, b_c picked through the nested -> natural index list)
+      SpmvOp s = B.base(Lv.Znat, kUserB);
+      s.aux = kUserB; s.aux_idx = Lv.d_inv + Lv.nf; s.alpha = 1.0; s.beta = 1.0;
+      s.out = c->bb + Lv.boff + Lv.nf; s.out_mode = 1;
+      B.push_spmv(s, Lv.Znat, 1, 1, 1);
+      c->prog.back().user = true;
+      c->n_head = (int)c->prog.size();
+      continue;
+    }
     if (Lv.any_c) B.push_ew(Lv.nc, c->bb + Lv.boff + Lv.nf, nullptr, nullptr, 1.0, Lv.bc_save, 1);
     SpmvOp s = B.base(Lv.Z, c->bb + Lv.boff);
     s.out = c->bb + Lv.boff + Lv.nf; s.out_mode = 2;
@@ -1225,6 +1274,12 @@ int build_program(Ctx *c) {
   for (int l = LB - 1; !c->full_smooth && l >= 1; --l) {
     Level &Lv = c->L[l];
     B.level = l;
+    if (l == 1 && c->io_fused) {
+      // exit permutation of the C points of level 1 (= every deeper level's result): one scatter into the caller's x
+      c->tail_begin = (int)c->prog.size();
+      B.push_ew(Lv.nc, c->xb + Lv.xoff + Lv.nf, nullptr, nullptr, 1.0, kUserX, 1, nullptr, Lv.d_inv + Lv.nf);
+      c->prog.back().user = true;
+    }
     int rc = B.emit_fc_richardson(Lv, true);
     if (rc) return rc;
     if (l == ldense) dense_end = (int)c->prog.size();
@@ -1259,6 +1314,7 @@ int build_program(Ctx *c) {
     for (const Op &o : sub) { d.bytes += o.bytes; d.nnz += o.nnz; }
     c->prog.erase(c->prog.begin() + dense_begin, c->prog.begin() + dense_end);
     c->prog.insert(c->prog.begin() + dense_begin, d);
+    if (c->tail_begin > dense_begin) c->tail_begin -= dense_end - dense_begin - 1;
     if (c->dense_level != ldense || c->dense_n != Ld.n) c->dense_built = false;
     c->dense_prog.swap(sub);
     c->dense_level = ldense; c->dense_n = Ld.n;
@@ -1376,7 +1432,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
   ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->full_smooth = c->full_smooth; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
-  ch->kernel = c->kernel; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+  ch->kernel = c->kernel; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
   for (int l = LA; l <= NL; ++l) {
@@ -1617,6 +1673,14 @@ int finalize_ctx(Ctx *c) {
         return fail(2, "level %d: rstart %lld does not match the ranks' row counts (%lld)", l, (long long)c->L[l].rstart, (long long)c->rangeV[l].start[c->rank]);
   }
 
+  // ---- entry / exit permutation fused into the level-1 ops: stand-alone serial Kaskade contexts whose level 1 is a
+  // pure F smooth (fuse_perm = 1: only where the permutation kernels cost something, n_1 > 16384; 2: always)
+  {
+    bool pure_f = NL >= 2 && !c->L[1].any_c && !c->L[1].smooth.empty() && c->L[1].smooth[0] > 0;
+    c->io_fused = pure_f && P == 1 && !c->cluster && c->own_stream && !c->full_smooth && c->device >= 0 &&
+                  (c->fuse_perm == 2 || (c->fuse_perm == 1 && c->L[1].n > 16384));
+  }
+
   // ---- coarse-level agglomeration (multi-rank): levels with few global rows move to rank 0
   c->l_agg = NL + 1;
   if (P > 1 && NL >= 2 && c->agg_rows > 0)
@@ -1706,7 +1770,12 @@ int finalize_ctx(Ctx *c) {
         }
         Zn.n_ghost = R.n_ghost; Zn.oia = R.oia; Zn.oja = R.oja; Zn.oa = R.oa; Zn.garray = R.garray;
         HostCSR Z = remap(Zn, pc.data(), nullptr, Lv.nf);
-        if ((rc = upload_csr(c, Z, &Lv.Z, SP_VF, l))) return rc;
+        if (l == 1 && c->io_fused) {
+          // natural column indices: the level-1 restriction gathers from the caller's b (is_f is increasing, so rows stay sorted)
+          for (int &cj : Z.ja) cj = Lv.is_f[cj];
+          Z.n = Lv.n;
+          if ((rc = upload_csr(c, Z, &Lv.Znat, SP_VF, l))) return rc;
+        } else if ((rc = upload_csr(c, Z, &Lv.Z, SP_VF, l))) return rc;
       }
       // P = [W; I] -> W with F-local rows, columns in level l+1 nested order
       const HostCSR &Pm = Lv.H[PFLARE_B200_P];
@@ -2003,13 +2072,24 @@ int apply_ctx(Ctx *c, const double *b, double *x, int on_device) {
     CUDA_TRY(cudaMemcpyAsync(c->io_b, b, (size_t)L1.n * 8, cudaMemcpyHostToDevice, c->stream));
     bd = c->io_b; xd = c->io_x;
   }
-  if ((rc = launch_ew_now(c, L1.n, bd, c->bb, L1.d_inv, nullptr, c->stream))) return rc;  // bb[p] = b[inv[p]]
-  if (c->use_graph && c->gexec) {
-    CUDA_TRY(cudaGraphLaunch(c->gexec, c->stream));
+  if (c->io_fused) {
+    // the level-1 ops read b / write x in natural ordering themselves: [head ops] [graph body] [tail ops]
+    if ((rc = run_program(c, c->stream, nullptr, 0, c->n_head, bd, xd))) return rc;
+    if (c->use_graph && c->gexec) {
+      CUDA_TRY(cudaGraphLaunch(c->gexec, c->stream));
+    } else {
+      if ((rc = run_program(c, c->stream, nullptr, c->n_head, c->tail_begin))) return rc;
+    }
+    if ((rc = run_program(c, c->stream, nullptr, c->tail_begin, -1, bd, xd))) return rc;
   } else {
-    if ((rc = run_program(c, c->stream, nullptr))) return rc;
+    if ((rc = launch_ew_now(c, L1.n, bd, c->bb, L1.d_inv, nullptr, c->stream))) return rc;  // bb[p] = b[inv[p]]
+    if (c->use_graph && c->gexec) {
+      CUDA_TRY(cudaGraphLaunch(c->gexec, c->stream));
+    } else {
+      if ((rc = run_program(c, c->stream, nullptr))) return rc;
+    }
+    if ((rc = launch_ew_now(c, L1.n, c->xb, xd, L1.d_pos, nullptr, c->stream))) return rc;  // x[i] = xb[pos[i]]
   }
-  if ((rc = launch_ew_now(c, L1.n, c->xb, xd, L1.d_pos, nullptr, c->stream))) return rc;  // x[i] = xb[pos[i]]
   if (!on_device) {
     CUDA_TRY(cudaMemcpyAsync(x, c->io_x, (size_t)L1.n * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -2330,7 +2410,7 @@ static void collect_stats(Ctx *c, double *v) {
   int nk = 0;
   for (size_t i = 0; i < c->prog.size(); ++i) {
     const Op &o = c->prog[i];
-    v[1] += o.kind == OPK_XCHG || o.kind == OPK_GATHER0 || o.kind == OPK_SCATTER0 ? 0.0 : o.bytes;
+    v[1] += (o.kind == OPK_XCHG || o.kind == OPK_GATHER0 || o.kind == OPK_SCATTER0 || (o.kind == OPK_EW && o.user)) ? 0.0 : o.bytes;   // exchanges and the exit scatter are not in the SURVEY.md 8d model
     v[2] += o.nnz;
     if (o.kind == OPK_SPMV || o.kind == OPK_EW) v[5] = std::max(v[5], o.bytes);
     if (!op_is_empty(o) && o.kind != OPK_CHILD) ++nk;
@@ -2347,8 +2427,7 @@ int pflare_b200_get_stats(void *handle, double *stats, int nstats) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
   double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   collect_stats(c, v);
-  v[0] += 2;  // + permute in / out
-  v[1] += 2.0 * 20.0 * (c->no_levels >= 1 ? c->L[1].n : 0);
+  if (!c->io_fused) v[0] += 2;  // + permute in / out (their bytes are not part of the SURVEY.md 8d model)
   for (int i = 0; i < nstats && i < 8; ++i) stats[i] = v[i];
   return 0;
 }
@@ -2362,15 +2441,13 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
   std::vector<cudaEvent_t> ev((size_t)n + 3);
   for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
   CUDA_TRY(cudaEventRecord(ev[0], c->stream));
-  if ((rc = launch_ew_now(c, L1.n, b_dev, c->bb, L1.d_inv, nullptr, c->stream))) return rc;   // entry permutation
+  if (!c->io_fused && (rc = launch_ew_now(c, L1.n, b_dev, c->bb, L1.d_inv, nullptr, c->stream))) return rc;   // entry permutation
   CUDA_TRY(cudaEventRecord(ev[1], c->stream));
-  std::vector<Ctx *> R{c};
-  std::vector<const std::vector<Op> *> Pp{&c->prog};
   for (int i = 0; i < n; ++i) {
-    if ((rc = exec_ops(R, Pp, i, i + 1, c->stream))) return rc;
+    if ((rc = run_program(c, c->stream, nullptr, i, i + 1, b_dev, x_dev))) return rc;
     CUDA_TRY(cudaEventRecord(ev[(size_t)i + 2], c->stream));
   }
-  if ((rc = launch_ew_now(c, L1.n, c->xb, x_dev, L1.d_pos, nullptr, c->stream))) return rc;   // exit permutation
+  if (!c->io_fused && (rc = launch_ew_now(c, L1.n, c->xb, x_dev, L1.d_pos, nullptr, c->stream))) return rc;   // exit permutation
   CUDA_TRY(cudaEventRecord(ev[(size_t)n + 2], c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   int cnt = 0;
@@ -2379,7 +2456,7 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
     CUDA_TRY(cudaEventElapsedTime(&t, ev[(size_t)(i + 1)], ev[(size_t)(i + 2)]));
     const bool perm = i < 0 || i == n;
     ms[cnt] = t;
-    bytes[cnt] = perm ? 20.0 * L1.n : c->prog[i].bytes;
+    bytes[cnt] = perm ? (c->io_fused ? 0.0 : 20.0 * L1.n) : c->prog[i].bytes;
     level[cnt] = perm ? 1 : c->prog[i].level;
     kind[cnt] = perm ? 6 : c->prog[i].tag;
     ++cnt;
@@ -2400,6 +2477,10 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else if (k == "full_smoothing_up_and_down") {
     if (c->finalized || c->planned) return fail(2, "full_smoothing_up_and_down must be set before finalize_setup");
     c->full_smooth = value != 0;
+  }
+  else if (k == "engine") {
+    if (value != 0 && value != 1) return fail(2, "engine must be 0 (TMA ring) or 1 (direct)");
+    c->engine = (int)value;
   }
   else if (k == "wt_stages") {
     if (value != 2 && value != 3) return fail(2, "wt_stages must be 2 or 3");
@@ -2430,7 +2511,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
     Ctx *ch = c->child.get();
-    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
     ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   }
   return 0;

@@ -35,12 +35,13 @@ def _device(H, **opts):
 
 
 @pytest.mark.parametrize("name", sorted(cases.CASES))
-@pytest.mark.parametrize("dense_rows", [0, 4096], ids=["sparse_all_levels", "dense_tail_default"])
-def test_vcycle_parity(built_libs, name, dense_rows):
+@pytest.mark.parametrize("mode", [dict(dense_rows=0), dict(dense_rows=4096), dict(fuse_perm=2), dict(fuse_perm=2, dense_rows=0, engine=0)],
+                         ids=["sparse_all_levels", "dense_tail_default", "fused_entry_exit_permutation", "fused_permutation_tma_ring_engine"])
+def test_vcycle_parity(built_libs, name, mode):
     A, H = cases.build(name)
     b = cases.rhs(A.shape[0])
     xo = _oracle(H).apply(b)
-    d = _device(H, dense_rows=dense_rows)
+    d = _device(H, **mode)
     x = d.apply(b)
     assert cases.rel_l2(x, xo) <= TOL, name
     # repeated applies are deterministic and do not depend on leftover state
@@ -54,6 +55,10 @@ def test_vcycle_parity(built_libs, name, dense_rows):
                                   # SpMV kernels: 0 = smem-staged CSR stream kernel, 1 = round-1 TMA kernel (CTA tiles), 2 = warp tiles (default)
                                   dict(kernel=0, dense_rows=0), dict(kernel=1, dense_rows=0), dict(kernel=2, dense_rows=0),
                                   dict(kernel=1, ctas_per_sm=1),
+                                  # kernel 2 engines: 1 = direct (no shared memory, default), 0 = TMA ring; entry / exit permutation fused into level 1
+                                  dict(engine=0, dense_rows=0), dict(engine=0), dict(engine=0, max_ctas=1, dense_rows=0), dict(engine=1, max_ctas=1, dense_rows=0),
+                                  dict(fuse_perm=2), dict(fuse_perm=2, graph=0, pdl=0), dict(fuse_perm=2, epi_classes=0, dense_rows=0), dict(fuse_perm=2, kernel=0), dict(fuse_perm=2, kernel=1, dense_rows=0),
+                                  dict(fuse_perm=0),
                                   # warp-tile kernel: ring depth, generic (run-time branched) epilogue instead of the compiled classes,
                                   # ONE persistent CTA per SM / in total (many tiles per warp: the mbarrier ring wraps many times)
                                   dict(wt_stages=3, dense_rows=0), dict(epi_classes=0, dense_rows=0), dict(epi_classes=0, fuse=0, dense_rows=0),
