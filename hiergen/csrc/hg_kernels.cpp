@@ -314,4 +314,70 @@ void hg_diag_dom_ratio(i64 n, const i32* ai, const i32* aj, const double* av, co
   }
 }
 
+
+// lAIR restrictor (incomplete SAI, /root/reference/src/SAI_Z.F90:24-640 with incomplete = .TRUE.): for every C row i
+// with F neighbourhood J = sparsity row i (sorted F-local indices), solve the square system
+//     A_ff(J, J)^T z = -A_cf(i, J)^T          (dense LU with partial pivoting, as the reference's gesv for |J| <= 40;
+//                                              larger neighbourhoods use the same direct solve here)
+// and store Z(i, J) = z.  zv has the sparsity pattern (si, sj).
+void hg_lair_z(i64 nc, const i32* si, const i32* sj, const i32* ffi, const i32* ffj, const double* ffv, const i32* cfi,
+               const i32* cfj, const double* cfv, double* zv) {
+#pragma omp parallel
+  {
+    std::vector<double> M, rhs;
+    std::vector<int> piv;
+#pragma omp for schedule(dynamic, 256)
+    for (i64 i = 0; i < nc; ++i) {
+      const int p0 = si[i], n = si[i + 1] - si[i];
+      if (n == 0) continue;
+      const i32* J = sj + p0;
+      M.assign((size_t)n * n, 0.0);
+      rhs.assign((size_t)n, 0.0);
+      // M = A_ff(J, J)^T  (row-major: M[r * n + c] = A_ff(J[c], J[r]))
+      for (int c = 0; c < n; ++c) {
+        const int row = J[c];
+        int q = 0;
+        for (int p = ffi[row]; p < ffi[row + 1]; ++p) {
+          const int col = ffj[p];
+          while (q < n && J[q] < col) ++q;
+          if (q < n && J[q] == col) M[(size_t)q * n + c] = ffv[p];
+        }
+      }
+      {  // rhs = -A_cf(i, J)
+        int q = 0;
+        for (int p = cfi[i]; p < cfi[i + 1]; ++p) {
+          const int col = cfj[p];
+          while (q < n && J[q] < col) ++q;
+          if (q < n && J[q] == col) rhs[q] = -cfv[p];
+        }
+      }
+      // Gaussian elimination with partial pivoting
+      for (int k = 0; k < n; ++k) {
+        int pv = k;
+        double best = std::fabs(M[(size_t)k * n + k]);
+        for (int r = k + 1; r < n; ++r)
+          if (std::fabs(M[(size_t)r * n + k]) > best) { best = std::fabs(M[(size_t)r * n + k]); pv = r; }
+        if (pv != k) {
+          for (int c = 0; c < n; ++c) std::swap(M[(size_t)k * n + c], M[(size_t)pv * n + c]);
+          std::swap(rhs[k], rhs[pv]);
+        }
+        const double d = M[(size_t)k * n + k];
+        if (d == 0.0) continue;
+        for (int r = k + 1; r < n; ++r) {
+          const double f = M[(size_t)r * n + k] / d;
+          if (f == 0.0) continue;
+          for (int c = k + 1; c < n; ++c) M[(size_t)r * n + c] -= f * M[(size_t)k * n + c];
+          rhs[r] -= f * rhs[k];
+        }
+      }
+      for (int k = n - 1; k >= 0; --k) {
+        double v = rhs[k];
+        for (int c = k + 1; c < n; ++c) v -= M[(size_t)k * n + c] * rhs[c];
+        const double d = M[(size_t)k * n + k];
+        rhs[k] = d != 0.0 ? v / d : 0.0;
+      }
+      for (int q = 0; q < n; ++q) zv[p0 + q] = rhs[q];
+    }
+  }
+}
 }  // extern "C"

@@ -179,3 +179,35 @@ def diag_dom_ratio(a, cf):
     L.hg_diag_dom_ratio(ctypes.c_int64(a.shape[0]), _p(ai, ctypes.c_int32), _p(aj, ctypes.c_int32), _p(av, ctypes.c_double),
                         cf8.ctypes.data_as(ctypes.POINTER(ctypes.c_byte)), _p(out, ctypes.c_double))
     return out
+
+
+def lair_z(A_ff, A_cf, sparsity):
+    """lAIR Z (incomplete SAI): Z(i, J) A_ff(J, J) = -A_cf(i, J) on the F neighbourhood J = sparsity row i
+    (/root/reference/src/SAI_Z.F90:24-640).  Returns Z with the pattern of ``sparsity``."""
+    L = lib()
+    S = sparsity.tocsr()
+    S.sort_indices()
+    ff = A_ff.tocsr(); ff.sort_indices()
+    cf = A_cf.tocsr(); cf.sort_indices()
+    si = np.ascontiguousarray(S.indptr, dtype=np.int32)
+    sj = np.ascontiguousarray(S.indices, dtype=np.int32)
+    zv = np.zeros(sj.size, dtype=np.float64)
+    if L is None:   # scipy / numpy fallback (small problems only)
+        ffc = ff.tocsc()
+        for i in range(S.shape[0]):
+            J = sj[si[i]:si[i + 1]]
+            if J.size == 0:
+                continue
+            M = ff[J][:, J].toarray()
+            rhs = -np.asarray(cf[i, J].todense()).ravel()
+            zv[si[i]:si[i + 1]] = np.linalg.solve(M.T, rhs)
+    else:
+        i32, f64 = ctypes.c_int32, ctypes.c_double
+        ffi = np.ascontiguousarray(ff.indptr, dtype=np.int32); ffj = np.ascontiguousarray(ff.indices, dtype=np.int32)
+        ffv = np.ascontiguousarray(ff.data, dtype=np.float64)
+        cfi = np.ascontiguousarray(cf.indptr, dtype=np.int32); cfj = np.ascontiguousarray(cf.indices, dtype=np.int32)
+        cfv = np.ascontiguousarray(cf.data, dtype=np.float64)
+        L.hg_lair_z.restype = None
+        L.hg_lair_z(ctypes.c_int64(S.shape[0]), _p(si, i32), _p(sj, i32), _p(ffi, i32), _p(ffj, i32), _p(ffv, f64),
+                    _p(cfi, i32), _p(cfj, i32), _p(cfv, f64), _p(zv, f64))
+    return _mk(zv, sj, si, S.shape)

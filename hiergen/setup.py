@@ -55,6 +55,10 @@ class AirOptions:
     # -pc_air_full_smoothing_up_and_down (AIR_Data_Type.F90:126-127): one Richardson sweep with an approximate
     # inverse of the WHOLE level matrix down and up (PCMG multiplicative V-cycle) instead of F/C smoothing on the way up
     full_smoothing_up_and_down: bool = False
+    # -pc_air_z_type product | lair (AIR_Data_Type.F90: z_type, lair_distance = 2): lAIR solves, per C point, the local
+    # system Z(i,J) A_ff(J,J) = -A_cf(i,J) on the distance-d F neighbourhood J (pattern of A_cf A_ff^(d-1))
+    z_type: str = "product"
+    lair_distance: int = 2
     seed: int = 1
 
     @property
@@ -310,9 +314,17 @@ def build_hierarchy(A, opts: AirOptions = None, verbose=False):
             W = native.spgemm(asm, A_fc_drop)
             W.data *= -1.0
             W = drop_small(W, opts.r_drop, relative=1)
-        # Z = -A_cf * inv(A_ff), drop
-        Z = native.spgemm(A_cf_drop, asm)
-        Z.data *= -1.0
+        if opts.z_type == "lair":
+            # lAIR (src/AIR_Operators_Setup.F90:699-779, src/SAI_Z.F90): neighbourhood from the dropped A_cf, A_ff,
+            # local solves with the undropped ones
+            pat = A_cf_drop
+            for _ in range(2, opts.lair_distance + 1):
+                pat = native.spgemm(pat, A_ff_drop)
+            Z = native.lair_z(A_ff, A_cf, pat)
+        else:
+            # Z = -A_cf * inv(A_ff), drop
+            Z = native.spgemm(A_cf_drop, asm)
+            Z.data *= -1.0
         Z = drop_small(Z, opts.r_drop, relative=1)
         R = compute_R_from_Z(Z, is_f, is_c, n)
         P = compute_P_from_W(W, is_f, is_c, n) if not opts.symmetric else _i32(R.T)

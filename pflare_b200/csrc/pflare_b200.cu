@@ -213,13 +213,13 @@ struct Ctx {
   // options
   int use_graph = 1, fuse = 1;
   int fuse_epi = 1;      // compile-time specialised epilogue classes (0: every op runs the generic epilogue)
-  int fuse_perm = 1;     // natural <-> nested permutation of b / x fused into the level-1 ops (serial Kaskade contexts)
+  int fuse_perm = 0;     // (measured slower: natural-order accesses interleave F and C points -> half-used sectors) natural <-> nested permutation of b / x fused into the level-1 ops (serial Kaskade contexts)
   bool io_fused = false; // decided at finalize_setup
   int n_head = 0, tail_begin = -1;   // program ops [0, n_head) and [tail_begin, end) reference the caller's vectors: launched per apply, outside the graph
   int full_smooth = 0;   // -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1), inv_A_ff(l) ~ A_l^-1 on all unknowns
   int dense_rows = 4096; // levels with <= this many rows are collapsed into one dense matrix (0 = off)
   int kernel = 2;        // 0: smem-staged stream kernel, 1: round-1 TMA kernel (CTA tiles), 2: warp-tile kernel
-  int engine = 1;        // kernel 2: 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel, no shared memory)
+  int engine = 2;        // kernel 2: 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
   int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
@@ -905,9 +905,22 @@ int launch_sv_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   CUDA_TRY(launch_k(c->pdl != 0, kern, grid, 256, 0, st, s));
   return 0;
 }
+template <int EPI, int KP, bool GH>
+int launch_thin_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  auto kern = spmv_thin_kernel<EPI, KP, GH>;
+  static int per_sm = 0;
+  int rc = kernel_per_sm(kern, 256, 0, &per_sm);
+  if (rc || dry) return rc;
+  const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
+  int grid = std::min((s.nwt + 7) / 8, c->num_sms * want);   // persistent, 8 warps per CTA
+  if (c->max_ctas > 0) grid = std::min(grid, c->max_ctas);
+  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, 256, 0, st, s));
+  return 0;
+}
 template <int EPI, int KP>
 int launch_wt_kp(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   const bool gh = s.xg != nullptr;
+  if (c->engine == 2) return gh ? launch_thin_inst<EPI, KP, true>(c, s, st, dry) : launch_thin_inst<EPI, KP, false>(c, s, st, dry);
   if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true>(c, s, st, dry) : launch_sv_inst<EPI, KP, false>(c, s, st, dry);
   if (c->wt_stages == 3) return gh ? launch_wt_inst<EPI, KP, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 3>(c, s, st, dry);
   return gh ? launch_wt_inst<EPI, KP, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 2>(c, s, st, dry);
@@ -1006,7 +1019,7 @@ int run_child(Ctx *c, cudaStream_t st) {
   if (!ch) return 0;
   Level &L1 = ch->L[1];
   int rc;
-  if ((rc = launch_ew_now(ch, L1.n, c->child_b, ch->bb, L1.d_inv, nullptr, st))) return rc;
+  if ((rc = launch_ew_now(ch, L1.n, c->child_b, ch->bb, nullptr, L1.d_pos, st))) return rc;
   if ((rc = run_program(ch, st, nullptr))) return rc;
   if ((rc = launch_ew_now(ch, L1.n, ch->xb, c->child_x, L1.d_pos, nullptr, st))) return rc;
   return 0;
@@ -2082,7 +2095,7 @@ int apply_ctx(Ctx *c, const double *b, double *x, int on_device) {
     }
     if ((rc = run_program(c, c->stream, nullptr, c->tail_begin, -1, bd, xd))) return rc;
   } else {
-    if ((rc = launch_ew_now(c, L1.n, bd, c->bb, L1.d_inv, nullptr, c->stream))) return rc;  // bb[p] = b[inv[p]]
+    if ((rc = launch_ew_now(c, L1.n, bd, c->bb, nullptr, L1.d_pos, c->stream))) return rc;  // bb[pos[i]] = b[i] (contiguous reads, a few sequential write streams)
     if (c->use_graph && c->gexec) {
       CUDA_TRY(cudaGraphLaunch(c->gexec, c->stream));
     } else {
@@ -2441,7 +2454,7 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
   std::vector<cudaEvent_t> ev((size_t)n + 3);
   for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
   CUDA_TRY(cudaEventRecord(ev[0], c->stream));
-  if (!c->io_fused && (rc = launch_ew_now(c, L1.n, b_dev, c->bb, L1.d_inv, nullptr, c->stream))) return rc;   // entry permutation
+  if (!c->io_fused && (rc = launch_ew_now(c, L1.n, b_dev, c->bb, nullptr, L1.d_pos, c->stream))) return rc;   // entry permutation
   CUDA_TRY(cudaEventRecord(ev[1], c->stream));
   for (int i = 0; i < n; ++i) {
     if ((rc = run_program(c, c->stream, nullptr, i, i + 1, b_dev, x_dev))) return rc;
@@ -2479,7 +2492,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
     c->full_smooth = value != 0;
   }
   else if (k == "engine") {
-    if (value != 0 && value != 1) return fail(2, "engine must be 0 (TMA ring) or 1 (direct)");
+    if (value != 0 && value != 1 && value != 2) return fail(2, "engine must be 0 (TMA ring), 1 (direct) or 2 (thin warps)");
     c->engine = (int)value;
   }
   else if (k == "wt_stages") {
@@ -2659,7 +2672,7 @@ int pflare_b200_cluster_apply(void *cluster, const double *const *b, double *con
     Level &L1 = c->L[1];
     const double *bd = b[r];
     if (!on_device) { CUDA_TRY(cudaMemcpyAsync(c->io_b, b[r], (size_t)L1.n * 8, cudaMemcpyHostToDevice, st)); bd = c->io_b; }
-    if ((rc = launch_ew_now(c, L1.n, bd, c->bb, L1.d_inv, nullptr, st))) return rc;
+    if ((rc = launch_ew_now(c, L1.n, bd, c->bb, nullptr, L1.d_pos, st))) return rc;
   }
   if (cl->gexec && cl->ranks[0]->use_graph) CUDA_TRY(cudaGraphLaunch(cl->gexec, st));
   else if ((rc = cluster_exec(cl, st))) return rc;
