@@ -53,7 +53,8 @@ struct SpmvOp {
   const unsigned char *blob;
   const WtDesc *wdesc;
   int nwt;
-  int kp;                      // slots per lane of a sub-tile (1, 2, 4, 8); a tile holds <= 8 / kp sub-tiles
+  int kp;                      // row-aligned format: slots per lane of a sub-tile (1, 2, 4, 8); chunk format: rows per lane of a tile
+  int fmt;                     // 1 = chunk format (spmv_wc_kernel), 2 = row-aligned format (spmv_wt / spmv_sv / spmv_thin kernels)
   int epi;                     // epilogue class
   // gather sources: column c < nloc reads x[c], otherwise xg[c - nloc] (ghost buffer)
   const double *x, *xg;
@@ -505,6 +506,158 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
       if (r < d.nrows) E::finish(op, d.r0 + r, rs_s[r], (XW && wf) ? xw_s[r] : 0.0, pc[q]);
     }
     __syncwarp();   // the row-sum buffer is reused by the next tile
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Chunk-format engine (wt_format.h, "CHUNK format"; operators with short rows): the same per-warp TMA ring as
+// spmv_wt_kernel, but lanes own consecutive runs of the CSR stream: every lane walks its kpl nonzeros, row ends
+// are flagged in per-lane masks, and ONE segmented warp scan carries the partial sum of a row that spans lanes.
+// Row sums go to shared memory (the consumed value area of the stage), the epilogue runs with RQ rows per lane.
+template <int EPI, int RQ, bool GHOST, int NW, int STAGES>
+__global__ void __launch_bounds__(NW * 32, 2) spmv_wc_kernel(const SpmvOp op) {
+  typedef EpiT<EPI> E;
+  typedef typename E::Pre Pre;
+  constexpr bool XW = E::kXw;
+  constexpr int KPL = kWcKpl;
+  constexpr bool AHEAD = E::kPre * RQ <= 16;   // epilogue operands prefetched one tile ahead (else at the start of stage B)
+  constexpr int XW_BYTES = XW ? RQ * 32 * 8 : 0;
+  constexpr int WARP_BYTES = STAGES * kWcStageBytes + XW_BYTES;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[NW][STAGES];
+  __shared__ WtDesc sdesc[NW][STAGES];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned char *wbase = smem_raw + (size_t)w * WARP_BYTES;
+  double *xw_s = reinterpret_cast<double *>(wbase + STAGES * kWcStageBytes);
+  const int nwarps = gridDim.x * NW;
+  const int first = blockIdx.x * NW + w;
+  const int my = first < op.nwt ? (op.nwt - first + nwarps - 1) / nwarps : 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[w][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint64_t pol = l2_policy_evict_first();
+  const WtDesc *__restrict__ wdesc = op.wdesc;
+  // producer (lane 0): one bulk copy per tile; the descriptor of the NEXT tile is fetched one issue ahead
+  WtDesc dn = {0u, 0, 0, 0};
+  if (lane == 0 && my > 0) dn = wdesc[first];
+  auto issue = [&](int j) {
+    const WtDesc d = dn;
+    if (j + 1 < my) dn = wdesc[(size_t)first + (size_t)(j + 1) * nwarps];
+    const int slot = j % STAGES;
+    sdesc[w][slot] = d;
+    const uint32_t bytes = (uint32_t)(d.geom * 384 + 64);
+    mbar_expect_tx(&full[w][slot], bytes);
+    tma_load_1d(wbase + slot * kWcStageBytes, op.blob + (size_t)d.off16 * 16, bytes, &full[w][slot], pol);
+  };
+  pdl_launch_dependents();
+  if (lane == 0)
+    for (int j = 0; j < STAGES && j < my; ++j) issue(j);   // matrix data only: legal before pdl_wait
+  pdl_wait();   // from here on the vectors written by the previous kernels are read
+  if (GHOST && lane == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+  __syncwarp();
+
+  const double *__restrict__ xv = op.x;
+  const double *__restrict__ xg = op.xg;
+  const int nloc = op.nloc;
+  WtDesc dnx = {0u, 0, 0, 0};
+  double xn[KPL];
+  Pre pn[RQ];
+  // stage A of tile j
+  auto stage_a = [&](int j) {
+    const int slot = j % STAGES;
+    mbar_wait(&full[w][slot], (uint32_t)((j / STAGES) & 1));
+    dnx = sdesc[w][slot];
+    const int *col_s = reinterpret_cast<const int *>(wbase + slot * kWcStageBytes + dnx.geom * 256);
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      xn[k] = 0.0;
+      if (k < dnx.geom) {
+        const int c = col_s[k * 32 + lane];
+        if (GHOST) xn[k] = (c >= nloc) ? __ldcg(xg + (c - nloc)) : xv[c];
+        else xn[k] = xv[c];
+      }
+    }
+    if (AHEAD) {
+#pragma unroll
+      for (int q = 0; q < RQ; ++q)
+        if (lane + 32 * q < dnx.nrows) pn[q] = E::prefetch(op, dnx.r0 + lane + 32 * q);
+    }
+  };
+  if (my > 0) stage_a(0);
+  for (int it = 0; it < my; ++it) {
+    const WtDesc d = dnx;
+    double p[KPL];
+    Pre pc[RQ];
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) p[k] = xn[k];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) pc[q] = pn[q];
+    if (it + 1 < my) stage_a(it + 1);
+    // ---- stage B
+    const int slot = it % STAGES;
+    unsigned char *st = wbase + slot * kWcStageBytes;
+    double *val_s = reinterpret_cast<double *>(st);
+    if (!AHEAD) {
+#pragma unroll
+      for (int q = 0; q < RQ; ++q)
+        if (lane + 32 * q < d.nrows) pc[q] = E::prefetch(op, d.r0 + lane + 32 * q);
+    }
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) p[k] = (k < d.geom) ? val_s[k * 32 + lane] * p[k] : 0.0;
+    const unsigned e = reinterpret_cast<const unsigned short *>(st + d.geom * 384)[lane];
+    __syncwarp();   // every lane holds its values: the value area now receives the row sums
+    // partial sum after this lane's last row end (the whole lane if it ends no row)
+    const int last = 31 - __clz((int)e);
+    double tail = 0.0;
+#pragma unroll
+    for (int k = 0; k < KPL; ++k)
+      if (k > last) tail += p[k];
+    // segmented inclusive scan of the tails over the lanes (a lane that ends a row starts a new segment)
+    const unsigned has = __ballot_sync(0xffffffffu, e != 0u);
+    const unsigned upto = has & (0xffffffffu >> (31 - lane));
+    const int dist = lane - (upto ? 31 - __clz((int)upto) : 0);
+    double sc = tail;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, sc, o);
+      if (o <= dist) sc += t;
+    }
+    double acc = __shfl_up_sync(0xffffffffu, sc, 1);   // the open row's partial sum entering this lane
+    if (lane == 0) acc = 0.0;
+    // first tile-local row index this lane finishes
+    const int cnt = __popc(e);
+    int rb = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, rb, o);
+      if (lane >= o) rb += t;
+    }
+    rb -= cnt;
+    const bool wl = (EPI == EPI_AFCW || EPI == EPI_AFCW_LOCAL) || (EPI == EPI_GENERIC && op.wlast);
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const bool end = (e >> k) & 1u;
+      if (XW && wl) {
+        if (end) { val_s[rb] = acc; xw_s[rb] = p[k]; ++rb; acc = 0.0; }
+        else acc += p[k];
+      } else {
+        acc += p[k];
+        if (end) { val_s[rb] = acc; ++rb; acc = 0.0; }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+      const int r = lane + 32 * q;
+      if (r < d.nrows) E::finish(op, d.r0 + r, val_s[r], (XW && wl) ? xw_s[r] : 0.0, pc[q]);
+    }
+    // generic-proxy accesses to this slot are done; order them before the next bulk copy into it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0 && it + STAGES < my) issue(it + STAGES);
   }
 }
 

@@ -120,7 +120,7 @@ struct DevCSR {
   // warp-tile storage (kernel 2): one blob per tile + descriptor list, interior tiles first
   unsigned char *blob = nullptr;
   WtDesc *wdesc = nullptr;
-  int nwt = 0, nwt_int = 0, kp = 8;
+  int nwt = 0, nwt_int = 0, kp = 8, fmt = 2;
   bool wt = false;         // this operator runs on the warp-tile kernel (no row longer than a tile)
   DevPlan *xp = nullptr;   // ghost exchange (multi-rank)
   bool is_set = false;
@@ -219,7 +219,9 @@ struct Ctx {
   int full_smooth = 0;   // -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1), inv_A_ff(l) ~ A_l^-1 on all unknowns
   int dense_rows = 4096; // levels with <= this many rows are collapsed into one dense matrix (0 = off)
   int kernel = 2;        // 0: smem-staged stream kernel, 1: round-1 TMA kernel (CTA tiles), 2: warp-tile kernel
-  int engine = 2;        // kernel 2: 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
+  int wt_format = 0;     // kernel 2 operator storage: 0 = by mean row length (fmt_split), 1 = chunk format, 2 = row-aligned lanes
+  double fmt_split = 4.5;
+  int engine = 1;        // kernel 2 (row-aligned format): 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
   int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
@@ -325,21 +327,40 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int s
     return fail(2, "operator has ghost columns but the context has a single rank");
   }
   if (c->device < 0) {  // host-only planning context (the warp-tile layout is still built when asked for: CPU-side checks)
-    if (getenv("PFLARE_B200_PLAN_BUILDS_TILES") && c->kernel == 2) { WtHost W; build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), wfirst, &W); }
+    if (getenv("PFLARE_B200_PLAN_BUILDS_TILES") && c->kernel == 2) {
+      WtHost W; build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), wfirst, &W);
+      WcHost V; build_wc(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), &V);
+    }
     return 0;
   }
   int rc;
   d->wt = false;
   if (c->kernel == 2) {
-    WtHost W;
-    build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), wfirst, &W);
-    if (W.ok) {
-      d->wt = true; d->kp = W.kp;
-      d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
-      if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
-      if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
-      d->ntiles = d->nwt; d->ntiles_int = d->nwt_int;
-      return 0;
+    // short rows: chunk format (no padding inside rows); longer rows: row-aligned lanes (coalesced gathers)
+    const double mean_len = h.m > 0 ? (double)h.nnz() / h.m : 0.0;
+    const bool chunk = c->wt_format == 1 || (c->wt_format == 0 && mean_len < c->fmt_split);
+    if (chunk) {
+      WcHost W;
+      build_wc(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), &W);
+      if (W.ok) {
+        d->wt = true; d->kp = W.rq; d->fmt = 1;
+        d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
+        if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
+        if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
+        d->ntiles = d->nwt; d->ntiles_int = d->nwt_int;
+        return 0;
+      }
+    } else {
+      WtHost W;
+      build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), wfirst, &W);
+      if (W.ok) {
+        d->wt = true; d->kp = W.kp; d->fmt = 2;
+        d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
+        if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
+        if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
+        d->ntiles = d->nwt; d->ntiles_int = d->nwt_int;
+        return 0;
+      }
     }
   }
   // CSR stream (kernel 0 / 1, or a row longer than a warp tile)
@@ -451,7 +472,7 @@ struct Builder {
     SpmvOp s{};
     s.rp = A.rp; s.col = A.col; s.val = A.val; s.m = A.m; s.nblk = A.nblk; s.blk = A.blk;
     s.tiles = A.tiles; s.ntiles = A.ntiles;
-    s.blob = A.blob; s.wdesc = A.wdesc; s.nwt = A.wt ? A.nwt : 0; s.kp = A.kp;
+    s.blob = A.blob; s.wdesc = A.wdesc; s.nwt = A.wt ? A.nwt : 0; s.kp = A.kp; s.fmt = A.fmt;
     s.x = x; s.nloc = A.n; s.beta = 1.0;
     s.xg = A.xp ? A.xp->d_xg : nullptr;
     return s;
@@ -925,8 +946,35 @@ int launch_wt_kp(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   if (c->wt_stages == 3) return gh ? launch_wt_inst<EPI, KP, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 3>(c, s, st, dry);
   return gh ? launch_wt_inst<EPI, KP, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 2>(c, s, st, dry);
 }
+// chunk-format engine: one instantiation per (epilogue class, rows per lane, ghost columns); TMA ring of 2 tiles
+template <int EPI, int RQ, bool GH>
+int launch_wc_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  constexpr int ST = 2;
+  auto kern = spmv_wc_kernel<EPI, RQ, GH, kWtWarps, ST>;
+  const size_t smem = (size_t)kWtWarps * (ST * kWcStageBytes + (EpiT<EPI>::kXw ? RQ * 32 * 8 : 0));
+  static int per_sm = 0;
+  int rc = kernel_per_sm(kern, kWtWarps * 32, smem, &per_sm);
+  if (rc || dry) return rc;
+  const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
+  int grid = std::min((s.nwt + kWtWarps - 1) / kWtWarps, c->num_sms * want);   // persistent
+  if (c->max_ctas > 0) grid = std::min(grid, c->max_ctas);
+  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, kWtWarps * 32, smem, st, s));
+  return 0;
+}
+template <int EPI>
+int launch_wc_epi(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  const bool gh = s.xg != nullptr;
+  switch (s.kp) {
+    case 1: return gh ? launch_wc_inst<EPI, 1, true>(c, s, st, dry) : launch_wc_inst<EPI, 1, false>(c, s, st, dry);
+    case 2: return gh ? launch_wc_inst<EPI, 2, true>(c, s, st, dry) : launch_wc_inst<EPI, 2, false>(c, s, st, dry);
+    case 4: return gh ? launch_wc_inst<EPI, 4, true>(c, s, st, dry) : launch_wc_inst<EPI, 4, false>(c, s, st, dry);
+    case 8: return gh ? launch_wc_inst<EPI, 8, true>(c, s, st, dry) : launch_wc_inst<EPI, 8, false>(c, s, st, dry);
+  }
+  return fail(7, "internal: rows per lane %d", s.kp);
+}
 template <int EPI>
 int launch_wt_epi(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  if (s.fmt == 1) return launch_wc_epi<EPI>(c, s, st, dry);
   switch (s.kp) {
     case 1: return launch_wt_kp<EPI, 1>(c, s, st, dry);
     case 2: return launch_wt_kp<EPI, 2>(c, s, st, dry);
@@ -1445,7 +1493,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
   ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->full_smooth = c->full_smooth; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
-  ch->kernel = c->kernel; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+  ch->kernel = c->kernel; ch->wt_format = c->wt_format; ch->fmt_split = c->fmt_split; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
   for (int l = LA; l <= NL; ++l) {
@@ -2490,6 +2538,15 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else if (k == "full_smoothing_up_and_down") {
     if (c->finalized || c->planned) return fail(2, "full_smoothing_up_and_down must be set before finalize_setup");
     c->full_smooth = value != 0;
+  }
+  else if (k == "wt_format") {
+    if (c->finalized || c->planned) return fail(2, "wt_format must be set before finalize_setup");
+    if (value != 0 && value != 1 && value != 2) return fail(2, "wt_format must be 0 (auto), 1 (chunk) or 2 (row-aligned lanes)");
+    c->wt_format = (int)value;
+  }
+  else if (k == "fmt_split") {
+    if (c->finalized || c->planned) return fail(2, "fmt_split must be set before finalize_setup");
+    c->fmt_split = value;
   }
   else if (k == "engine") {
     if (value != 0 && value != 1 && value != 2) return fail(2, "engine must be 0 (TMA ring), 1 (direct) or 2 (thin warps)");

@@ -158,7 +158,8 @@ def test_warp_tile_format_and_row_sum_algorithm(tmp_path):
     (lane-local walk + segmented warp scan), emulated lane by lane on the CPU against a plain CSR product:
     random row lengths 1..256, empty rows, the merged A_fc|W (last entry = W) mode, ghost columns."""
     import subprocess
-    exe = str(tmp_path / "wt_format_check")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-o", exe, os.path.join(ROOT, "tests", "c", "wt_format_check.cpp")])
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "WT_FORMAT_OK" in out.stdout, out.stdout + out.stderr
+    for name, ok in (("wt_format_check", "WT_FORMAT_OK"), ("wc_format_check", "WC_FORMAT_OK")):   # row-aligned lanes / chunk format
+        exe = str(tmp_path / name)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-o", exe, os.path.join(ROOT, "tests", "c", name + ".cpp")])
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and ok in out.stdout, out.stdout + out.stderr

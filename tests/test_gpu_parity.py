@@ -57,7 +57,7 @@ def test_vcycle_parity(built_libs, name, mode):
                                   dict(kernel=1, ctas_per_sm=1),
                                   # kernel 2 engines: 1 = direct (no shared memory, default), 0 = TMA ring; entry / exit permutation fused into level 1
                                   dict(engine=0, dense_rows=0), dict(engine=0), dict(engine=0, max_ctas=1, dense_rows=0), dict(engine=1, max_ctas=1, dense_rows=0),
-                                  dict(engine=1, dense_rows=0), dict(engine=1), dict(engine=2, max_ctas=1, dense_rows=0), dict(engine=2, epi_classes=0, dense_rows=0), dict(engine=1, fuse_perm=2),
+                                  dict(engine=1, dense_rows=0), dict(engine=1), dict(wt_format=1, dense_rows=0), dict(wt_format=2, dense_rows=0), dict(wt_format=1, max_ctas=1, dense_rows=0), dict(wt_format=2, engine=2), dict(engine=2, max_ctas=1, dense_rows=0), dict(engine=2, epi_classes=0, dense_rows=0), dict(engine=1, fuse_perm=2),
                                   dict(fuse_perm=2), dict(fuse_perm=2, graph=0, pdl=0), dict(fuse_perm=2, epi_classes=0, dense_rows=0), dict(fuse_perm=2, kernel=0), dict(fuse_perm=2, kernel=1, dense_rows=0),
                                   dict(fuse_perm=0),
                                   # warp-tile kernel: ring depth, generic (run-time branched) epilogue instead of the compiled classes,
