@@ -137,6 +137,23 @@ int pflare_b200_inv_apply(void *handle, int our_level, int which, const double *
  * from b; natural ordering of that level; same pointer convention. */
 int pflare_b200_fc_smooth(void *handle, int our_level, const double *b, double *x, int on_device);
 
+/* Outer Krylov method on the device: the KSPSolve the reference's drivers run around PCApply
+ * (tests/Makefile:537-546, 1128-1134, 1322-1323; tests/adv_diff_fd.c: KSPGMRES, restart 30, b = 0, x0 = 1).
+ * pflare_b200_ksp_set_operator hands over the system matrix (level-1 MPIAIJ blocks, natural numbering, same
+ * conventions as pflare_b200_set_csr); it must be called before finalize_setup.  pflare_b200_ksp_solve runs
+ *   ksp_type 0: KSPGMRES (restart <= 30, classical Gram-Schmidt), pc_side 0 = left, 1 = right
+ *   ksp_type 1: KSPRICHARDSON (unpreconditioned norm)
+ * with KSPConvergedDefault (||r|| <= max(rtol ||b||, atol); zero rhs and nonzero guess: rtol ||r0||), preconditioned
+ * by the handle's V-cycle (no_levels >= 2) or its inverse (PCPFLAREINV handle, no_levels == 1).  x holds the
+ * initial guess on entry and the solution on exit.  *its = iterations PETSc would report, *reason = 2 (rtol) /
+ * 3 (atol) / -3 (max_it reached) as in KSPConvergedReason, *rnorm = last residual norm estimate.  Vectors, products,
+ * V-cycles and all vector updates stay on the device; only the Gram-Schmidt scalars travel to the host. */
+int pflare_b200_ksp_set_operator(void *handle, int m, int n_local_cols, int64_t cstart, const int *di, const int *dj,
+                                 const double *da, int n_ghost, const int *oi, const int *oj, const double *oa,
+                                 const int64_t *garray);
+int pflare_b200_ksp_solve(void *handle, int ksp_type, int pc_side, double rtol, double atol, int max_it, int restart,
+                          const double *b, double *x, int on_device, int *its, int *reason, double *rnorm);
+
 /* The CUDA stream (cudaStream_t) all device work of this handle is ordered on. */
 int pflare_b200_get_stream(void *handle, void **stream);
 int pflare_b200_synchronize(void *handle);

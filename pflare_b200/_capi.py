@@ -30,6 +30,8 @@ SIGNATURES = {
     "pflare_b200_apply": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "pflare_b200_inv_apply": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int]),
     "pflare_b200_fc_smooth": (c_int, [c_vp, c_int, c_vp, c_vp, c_int]),
+    "pflare_b200_ksp_set_operator": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "pflare_b200_ksp_solve": (c_int, [c_vp, c_int, c_int, c_dbl, c_dbl, c_int, c_int, c_vp, c_vp, c_int, P(c_int), P(c_int), P(c_dbl)]),
     "pflare_b200_get_stream": (c_int, [c_vp, P(c_vp)]),
     "pflare_b200_synchronize": (c_int, [c_vp]),
     "pflare_b200_get_is": (c_int, [c_vp, c_int, c_int, c_vp]),

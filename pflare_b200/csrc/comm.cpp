@@ -13,6 +13,7 @@ typedef int (*fn_init)(void **, int, UniqueId, int);
 typedef int (*fn_destroy)(void *);
 typedef int (*fn_sendrecv)(void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*fn_void)(void);
+typedef int (*fn_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef const char *(*fn_errstr)(int);
 
 struct Api {
@@ -22,6 +23,7 @@ struct Api {
   fn_destroy destroy = nullptr;
   fn_sendrecv send = nullptr, recv = nullptr;
   fn_void gstart = nullptr, gend = nullptr;
+  fn_allreduce allreduce = nullptr;
   fn_errstr errstr = nullptr;
   std::string load_error;
 };
@@ -43,6 +45,7 @@ Api &api() {
     a.recv = (fn_sendrecv)dlsym(a.lib, "ncclRecv");
     a.gstart = (fn_void)dlsym(a.lib, "ncclGroupStart");
     a.gend = (fn_void)dlsym(a.lib, "ncclGroupEnd");
+    a.allreduce = (fn_allreduce)dlsym(a.lib, "ncclAllReduce");
     a.errstr = (fn_errstr)dlsym(a.lib, "ncclGetErrorString");
     if (!a.get_uid || !a.init || !a.destroy || !a.send || !a.recv || !a.gstart || !a.gend)
       a.load_error = "libnccl is missing required symbols";
@@ -91,6 +94,10 @@ bool Comm::group_start(std::string *err) { return ok(api().gstart(), "ncclGroupS
 bool Comm::group_end(std::string *err) { return ok(api().gend(), "ncclGroupEnd", err); }
 bool Comm::send(const void *buf, size_t count, int dtype_bytes, int peer, cudaStream_t st, std::string *err) {
   return ok(api().send((void *)buf, count, nccl_type(dtype_bytes), peer, comm_, st), "ncclSend", err);
+}
+bool Comm::allreduce_sum(const double *in, double *out, size_t count, cudaStream_t st, std::string *err) {
+  if (!api().allreduce) { if (err) *err = "libnccl has no ncclAllReduce"; return false; }
+  return ok(api().allreduce(in, out, count, 8 /*ncclFloat64*/, 0 /*ncclSum*/, comm_, st), "ncclAllReduce", err);
 }
 bool Comm::recv(void *buf, size_t count, int dtype_bytes, int peer, cudaStream_t st, std::string *err) {
   return ok(api().recv(buf, count, nccl_type(dtype_bytes), peer, comm_, st), "ncclRecv", err);

@@ -19,6 +19,8 @@ class Comm {
   bool group_end(std::string *err);
   bool send(const void *buf, size_t count, int dtype_bytes, int peer, cudaStream_t st, std::string *err);
   bool recv(void *buf, size_t count, int dtype_bytes, int peer, cudaStream_t st, std::string *err);
+  // outer Krylov method only (dot products / norms): the V-cycle itself needs no reduction
+  bool allreduce_sum(const double *in, double *out, size_t count, cudaStream_t st, std::string *err);
 
  private:
   Comm() {}

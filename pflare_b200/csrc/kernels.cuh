@@ -1032,6 +1032,62 @@ __global__ void store_column_kernel(int n, int j, const double *v, double *T) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) T[(size_t)i * n + j] = v[i];
 }
 
+// ---- BLAS-1 of the outer Krylov method (KSPGMRES with classical Gram-Schmidt / KSPRICHARDSON around PCApply)
+constexpr int kKspMaxVec = 32;     // restart + 2 <= 32 basis vectors per multi-dot / multi-axpy
+struct KspCoef { double c[kKspMaxVec]; };
+// partial[cta][i] = sum over the CTA's elements of w[j] * V[i][j], i < nv: ONE pass over w and the basis
+// (fixed grid and fixed order inside a CTA -> deterministic)
+__global__ void __launch_bounds__(kThreads) multi_dot_kernel(int n, const double *__restrict__ w, const double *__restrict__ V, long long ld,
+                                                             int nv, double *__restrict__ partial) {
+  __shared__ double red[kThreads / 32][kKspMaxVec];
+  double acc[kKspMaxVec];
+#pragma unroll
+  for (int i = 0; i < kKspMaxVec; ++i) acc[i] = 0.0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const double wj = w[j];
+#pragma unroll
+    for (int i = 0; i < kKspMaxVec; ++i)
+      if (i < nv) acc[i] += wj * V[(size_t)i * ld + j];
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kKspMaxVec; ++i) {
+    if (i < nv) {
+      double v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) red[wp][i] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nv) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) v += red[k][threadIdx.x];
+    partial[(size_t)blockIdx.x * kKspMaxVec + threadIdx.x] = v;
+  }
+}
+// out[i] = sum_cta partial[cta][i] in CTA order
+__global__ void multi_dot_finish_kernel(int ncta, int nv, const double *__restrict__ partial, double *__restrict__ out) {
+  const int i = threadIdx.x;
+  if (i < nv) {
+    double v = 0.0;
+    for (int k = 0; k < ncta; ++k) v += partial[(size_t)k * kKspMaxVec + i];
+    out[i] = v;
+  }
+}
+// y[j] = beta * y[j] + sum_i co.c[i] * V[i][j]
+__global__ void __launch_bounds__(kThreads) multi_axpy_kernel(int n, double *__restrict__ y, double beta, const double *__restrict__ V,
+                                                              long long ld, int nv, const KspCoef co) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double v = beta != 0.0 ? beta * y[j] : 0.0;
+#pragma unroll
+    for (int i = 0; i < kKspMaxVec; ++i)
+      if (i < nv) v += co.c[i] * V[(size_t)i * ld + j];
+    y[j] = v;
+  }
+}
+
 // ---- peer-memory ghost exchange (one process per GPU with IPC-mapped arenas, or an in-process group)
 struct PushOp {
   int n;                        // entries to push

@@ -87,7 +87,8 @@ struct HostCSR {
 // requested index into a position of the vector segment the operator reads)
 enum { SP_F = 0,      // global F numbering of a level: position = F-local index
        SP_VNEST = 1,  // global natural numbering of a level whose local vector is read in nested order
-       SP_VF = 2 };   // global natural numbering of a level, only F points allowed, position = F-local index
+       SP_VF = 2,     // global natural numbering of a level, only F points allowed, position = F-local index
+       SP_NAT = 3 };  // global natural numbering of a level whose local vector is read in NATURAL order (outer Krylov operator)
 
 struct DevPlan {
   GhostPlan plan;
@@ -220,7 +221,7 @@ struct Ctx {
   int dense_rows = 4096; // levels with <= this many rows are collapsed into one dense matrix (0 = off)
   int kernel = 2;        // 0: smem-staged stream kernel, 1: round-1 TMA kernel (CTA tiles), 2: warp-tile kernel
   int wt_format = 0;     // kernel 2 operator storage: 0 = by mean row length (fmt_split), 1 = chunk format, 2 = row-aligned lanes
-  double fmt_split = 4.5;
+  double fmt_split = 8.0;   // measured on the 4096^2 cycle: 3 -> 2.82 ms, 4.5 -> 2.65 ms, 8 -> 2.62 ms
   int engine = 1;        // kernel 2 (row-aligned format): 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
   int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
@@ -234,6 +235,12 @@ struct Ctx {
   Cluster *cluster = nullptr;            // in-process group of ranks (lockstep execution on one stream)
   std::deque<DevPlan> plans;
   std::vector<Ranges> rangeV, rangeF;    // per level (1-based): ownership of natural rows / of F points
+  // outer Krylov method (pflare_b200_ksp_*): the system matrix in natural ordering + work vectors
+  HostCSR ksp_A;
+  DevCSR ksp_Ad;
+  double *ksp_buf = nullptr; size_t ksp_cap = 0;      // basis V (restart + 1 vectors) + w, z, u
+  double *ksp_partial = nullptr, *ksp_dots = nullptr; // multi-dot partials / results
+  double *ksp_hdots = nullptr;                        // pinned host copy of the dots
   int l_agg = 0;                         // first agglomerated level (no_levels + 1: none)
   int n_dist = 0;                        // number of distributed levels with an F/C structure (l < min(l_agg, NL))
   std::unique_ptr<Ctx> child;            // rank 0: serial hierarchy of the agglomerated levels
@@ -1668,6 +1675,7 @@ void release_device_state(Ctx *c) {
   for (double *&p : c->scr) p = nullptr;
   c->child_b = c->child_x = nullptr;
   c->arena = nullptr; c->arena_bytes = 0; c->p2p_ready = false; c->d_peer_flags = nullptr; c->d_done = nullptr;
+  c->ksp_Ad = DevCSR(); c->ksp_buf = nullptr; c->ksp_cap = 0; c->ksp_partial = c->ksp_dots = nullptr;
   for (Level &Lv : c->L) {
     for (DevCSR *A : {&Lv.Z, &Lv.W, &Lv.Afc, &Lv.Afcw, &Lv.Aff, &Lv.Acf, &Lv.Acc, &Lv.Coarse, &Lv.Pn, &Lv.Znat, &Lv.inv_ff.d, &Lv.inv_cc.d}) *A = DevCSR();
     Lv.inv_ff.ddiag = Lv.inv_cc.ddiag = nullptr;
@@ -1991,6 +1999,13 @@ int finalize_ctx(Ctx *c) {
     }
   }
 
+  // ---- the outer Krylov method's system matrix (natural ordering: KSP vectors are the caller's vectors)
+  if (c->ksp_A.set) {
+    if (c->ksp_A.m != c->L[1].n) return fail(2, "ksp operator has %d rows, level 1 has %d", c->ksp_A.m, c->L[1].n);
+    HostCSR A2 = remap(c->ksp_A, nullptr, nullptr, c->L[1].n);
+    if ((rc = upload_csr(c, A2, &c->ksp_Ad, SP_NAT, 1))) return rc;
+  }
+
   // ---- X3: ghost exchange plans (multi-rank): who needs which entries of whose vector segments
   if (P > 1) {
     std::vector<std::vector<char>> out((size_t)P), in;
@@ -2025,7 +2040,7 @@ int finalize_ctx(Ctx *c) {
           const int idx = r.get<int32_t>();
           int posn = -1;
           if (D.space_kind == SP_F) { if (idx >= 0 && idx < Ls.nf) posn = idx; }
-          else if (idx >= 0 && idx < Ls.n) posn = D.space_kind == SP_VNEST ? Ls.pos[idx] : Ls.fpos[idx];
+          else if (idx >= 0 && idx < Ls.n) posn = D.space_kind == SP_VNEST ? Ls.pos[idx] : (D.space_kind == SP_NAT ? idx : Ls.fpos[idx]);
           if (posn < 0) return fail(24, "rank %d requested an entry this rank cannot serve (operator %d)", q, op);
           D.plan.send_idx.push_back(posn);
         }
@@ -2393,6 +2408,227 @@ int pflare_b200_fc_smooth(void *handle, int our_level, const double *b, double *
   return 0;
 }
 
+// ---------------------------------------------------------------------- outer Krylov method on the device
+// KSPSolve as the reference's drivers run it around PCApply (tests/Makefile:537-546, 1128-1134, 1322-1323):
+// KSPGMRES (restart 30, classical Gram-Schmidt, left or right preconditioning) or preconditioned KSPRICHARDSON,
+// KSPConvergedDefault (||r|| <= max(rtol ||b||, atol); zero rhs with a nonzero guess: rtol ||r0||).  Vectors,
+// SpMV, the V-cycle and all BLAS-1 stay on the device; per iteration only the k + 2 Gram-Schmidt scalars cross
+// to the host (as in PETSc's own GPU back ends).  Multi-rank: one ncclAllReduce per reduction.
+int pflare_b200_ksp_set_operator(void *handle, int m, int n_local_cols, int64_t cstart, const int *di, const int *dj, const double *da,
+                                 int n_ghost, const int *oi, const int *oj, const double *oa, const int64_t *garray) {
+  Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  HostCSR *H = &c->ksp_A;
+  H->set = true; H->m = m; H->n = n_local_cols; H->cstart = cstart;
+  H->ia.assign(di, di + m + 1);
+  H->ja.assign(dj, dj + di[m]);
+  H->a.assign(da, da + di[m]);
+  H->n_ghost = n_ghost;
+  H->oia.clear(); H->oja.clear(); H->oa.clear(); H->garray.clear();
+  if (n_ghost > 0) {
+    H->oia.assign(oi, oi + m + 1);
+    H->oja.assign(oj, oj + oi[m]);
+    H->oa.assign(oa, oa + oi[m]);
+    H->garray.assign(garray, garray + n_ghost);
+  }
+  c->finalized = false;
+  return 0;
+}
+
+namespace {
+struct Ksp {
+  Ctx *c;
+  int n;
+  cudaStream_t st;
+  double *V, *w, *z, *u;   // basis (ld = n), work vectors
+  int ncta;
+  // y = alpha * aux + beta * A x   (aux may be null)
+  int matmult(const double *x, double *y, const double *aux, double alpha, double beta) {
+    std::vector<Op> ops;
+    Builder B{c, &ops};
+    B.level = 1;
+    SpmvOp s = B.base(c->ksp_Ad, x);
+    s.aux = aux; s.alpha = alpha; s.beta = beta;
+    s.out = y; s.out_mode = 1;
+    B.push_spmv(s, c->ksp_Ad, 4, aux ? 1 : 0, 1);
+    std::vector<Ctx *> R{c};
+    std::vector<const std::vector<Op> *> P{&ops};
+    return exec_ops(R, P, 0, (int)ops.size(), st);
+  }
+  // y = M x : the handle's preconditioner (V-cycle, or the single inverse of a PCPFLAREINV handle)
+  int pcapply(const double *x, double *y) {
+    if (c->no_levels >= 2) return apply_ctx(c, x, y, 1);
+    std::vector<Op> ops;
+    int nn = 0; const int *perm, *iperm;
+    int rc = build_inv_ops(c, 1, PFLARE_B200_INV_AFF, &ops, &nn, &perm, &iperm, x, y);
+    if (rc) return rc;
+    std::vector<Ctx *> R{c};
+    std::vector<const std::vector<Op> *> P{&ops};
+    return exec_ops(R, P, 0, (int)ops.size(), st);
+  }
+  // out[i] = <a, Vb_i>, i < nv (global sums)
+  int dots(const double *a, const double *Vb, int nv, double *out) {
+    multi_dot_kernel<<<ncta, kThreads, 0, st>>>(n, a, Vb, (long long)n, nv, c->ksp_partial);
+    multi_dot_finish_kernel<<<1, kKspMaxVec, 0, st>>>(ncta, nv, c->ksp_partial, c->ksp_dots);
+    CUDA_TRY(cudaGetLastError());
+    if (c->nranks > 1) {
+      std::string err;
+      if (!c->comm || !c->comm->allreduce_sum(c->ksp_dots, c->ksp_dots, (size_t)nv, st, &err)) return fail(21, "ksp reduction: %s", err.c_str());
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->ksp_hdots, c->ksp_dots, sizeof(double) * (size_t)nv, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < nv; ++i) out[i] = c->ksp_hdots[i];
+    return 0;
+  }
+  int norm(const double *a, double *out) {
+    double v = 0.0;
+    int rc = dots(a, a, 1, &v);
+    *out = std::sqrt(v);
+    return rc;
+  }
+  // y = beta * y + sum_i co[i] * Vb_i
+  int axpys(double *y, double beta, const double *Vb, int nv, const double *co) {
+    KspCoef k;
+    for (int i = 0; i < kKspMaxVec; ++i) k.c[i] = i < nv ? co[i] : 0.0;
+    multi_axpy_kernel<<<ncta, kThreads, 0, st>>>(n, y, beta, Vb, (long long)n, nv, k);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+};
+}  // namespace
+
+int pflare_b200_ksp_solve(void *handle, int ksp_type, int pc_side, double rtol, double atol, int max_it, int restart, const double *b,
+                          double *x, int on_device, int *its_out, int *reason, double *rnorm_out) {
+  Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
+  if (c->device < 0) return fail(10, "host-only planning context: no CUDA device bound, and this library has no CPU fallback");
+  if (!c->finalized) return fail(6, "ksp_solve called before finalize_setup");
+  if (c->cluster) return fail(2, "ksp_solve is not available on an in-process rank group");
+  if (!c->ksp_Ad.valid()) return fail(6, "ksp_solve needs the system matrix: call pflare_b200_ksp_set_operator before finalize_setup");
+  if (restart < 1 || restart + 2 > kKspMaxVec) return fail(2, "restart must be in 1..%d", kKspMaxVec - 2);
+  if (ksp_type != 0 && ksp_type != 1) return fail(2, "ksp_type must be 0 (gmres) or 1 (richardson)");
+  const int n = c->L[1].n;
+  const size_t need = (size_t)(restart + 1 + 3) * (size_t)std::max(n, 1) + (on_device ? 0 : 2 * (size_t)std::max(n, 1));
+  if (c->ksp_cap < need) {
+    if ((rc = dev_alloc(c, &c->ksp_buf, need))) return rc;
+    c->ksp_cap = need;
+  }
+  Ksp K;
+  K.c = c; K.n = n; K.st = c->stream;
+  K.ncta = std::max(1, std::min((n + kThreads - 1) / kThreads, c->num_sms * 4));
+  if (!c->ksp_partial) {
+    if ((rc = dev_alloc(c, &c->ksp_partial, (size_t)c->num_sms * 4 * kKspMaxVec))) return rc;
+    if ((rc = dev_alloc(c, &c->ksp_dots, (size_t)kKspMaxVec))) return rc;
+  }
+  if (!c->ksp_hdots) CUDA_TRY(cudaMallocHost((void **)&c->ksp_hdots, sizeof(double) * kKspMaxVec));
+  K.V = c->ksp_buf;
+  K.w = K.V + (size_t)(restart + 1) * n;
+  K.z = K.w + n;
+  K.u = K.z + n;
+  const double *bd = b;
+  double *xd = x;
+  if (!on_device) {
+    double *hb = K.u + n, *hx = hb + n;
+    CUDA_TRY(cudaMemcpyAsync(hb, b, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(hx, x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    bd = hb; xd = hx;
+  }
+  const bool left = pc_side == 0;
+  int its = 0, why = 0;
+  double ref = -1.0, rn = 0.0;
+  const double one = 1.0;
+  if (ksp_type == 1) {
+    // KSPRICHARDSON, unpreconditioned norm: x += M (b - A x)
+    double bn;
+    if ((rc = K.matmult(xd, K.w, bd, 1.0, -1.0))) return rc;            // r = b - A x
+    if ((rc = K.norm(bd, &bn))) return rc;
+    if ((rc = K.norm(K.w, &rn))) return rc;
+    ref = bn > 0 ? bn : rn;
+    for (int it = 0;; ++it) {
+      if (rn <= std::max(rtol * ref, atol)) { why = rn <= atol && !(rn <= rtol * ref) ? 3 : 2; its = it; break; }
+      if (it == max_it) { why = -3; its = max_it; break; }
+      if ((rc = K.pcapply(K.w, K.z))) return rc;
+      if ((rc = K.axpys(xd, 1.0, K.z, 1, &one))) return rc;             // x += z
+      if ((rc = K.matmult(xd, K.w, bd, 1.0, -1.0))) return rc;
+      if ((rc = K.norm(K.w, &rn))) return rc;
+    }
+  } else {
+    std::vector<double> H((size_t)(restart + 1) * restart, 0.0), g((size_t)restart + 1), cs((size_t)restart), sn((size_t)restart), hcol((size_t)restart + 2);
+    auto Hat = [&](int i, int k) -> double & { return H[(size_t)i * restart + k]; };
+    while (true) {
+      // r = b - A x (left: M r)
+      if ((rc = K.matmult(xd, K.w, bd, 1.0, -1.0))) return rc;
+      double *r = K.w;
+      if (left) { if ((rc = K.pcapply(K.w, K.z))) return rc; r = K.z; }
+      double beta;
+      if ((rc = K.norm(r, &beta))) return rc;
+      if (ref < 0) {
+        double bn;
+        if (left) { if ((rc = K.pcapply(bd, K.u))) return rc; if ((rc = K.norm(K.u, &bn))) return rc; }
+        else if ((rc = K.norm(bd, &bn))) return rc;
+        ref = bn > 0 ? bn : beta;
+        rn = beta;
+        if (beta <= std::max(rtol * ref, atol)) { why = 2; break; }
+      }
+      { const double inv = 1.0 / beta; if ((rc = K.axpys(K.V, 0.0, r, 1, &inv))) return rc; }   // V_0 = r / beta
+      std::fill(H.begin(), H.end(), 0.0);
+      std::fill(g.begin(), g.end(), 0.0);
+      g[0] = beta;
+      int kdone = 0;
+      bool conv = false;
+      for (int k = 0; k < restart; ++k) {
+        double *Vk = K.V + (size_t)k * n, *Vk1 = K.V + (size_t)(k + 1) * n;
+        if (left) { if ((rc = K.matmult(Vk, K.z, nullptr, 0.0, 1.0))) return rc; if ((rc = K.pcapply(K.z, K.w))) return rc; }
+        else { if ((rc = K.pcapply(Vk, K.z))) return rc; if ((rc = K.matmult(K.z, K.w, nullptr, 0.0, 1.0))) return rc; }
+        // classical Gram-Schmidt: all projections from the same w, then one update
+        if ((rc = K.dots(K.w, K.V, k + 1, hcol.data()))) return rc;
+        for (int i = 0; i <= k; ++i) { Hat(i, k) = hcol[i]; hcol[i] = -hcol[i]; }
+        if ((rc = K.axpys(K.w, 1.0, K.V, k + 1, hcol.data()))) return rc;
+        double hn;
+        if ((rc = K.norm(K.w, &hn))) return rc;
+        Hat(k + 1, k) = hn;
+        if (hn != 0.0) { const double inv = 1.0 / hn; if ((rc = K.axpys(Vk1, 0.0, K.w, 1, &inv))) return rc; }
+        for (int i = 0; i < k; ++i) {
+          const double t = cs[i] * Hat(i, k) + sn[i] * Hat(i + 1, k);
+          Hat(i + 1, k) = -sn[i] * Hat(i, k) + cs[i] * Hat(i + 1, k);
+          Hat(i, k) = t;
+        }
+        const double d = std::hypot(Hat(k, k), Hat(k + 1, k));
+        cs[k] = Hat(k, k) / d; sn[k] = Hat(k + 1, k) / d;
+        Hat(k, k) = d; Hat(k + 1, k) = 0.0;
+        g[k + 1] = -sn[k] * g[k]; g[k] = cs[k] * g[k];
+        ++its; kdone = k + 1;
+        rn = std::fabs(g[k + 1]);
+        if (rn <= std::max(rtol * ref, atol)) { conv = true; break; }
+        if (its >= max_it) break;
+      }
+      // y = H^-1 g ; x += V y (right: x += M V y)
+      std::vector<double> y((size_t)kdone, 0.0);
+      for (int i = kdone - 1; i >= 0; --i) {
+        double v = g[i];
+        for (int j = i + 1; j < kdone; ++j) v -= Hat(i, j) * y[j];
+        y[i] = v / Hat(i, i);
+      }
+      if (kdone > 0) {
+        if (left) { if ((rc = K.axpys(xd, 1.0, K.V, kdone, y.data()))) return rc; }
+        else {
+          if ((rc = K.axpys(K.u, 0.0, K.V, kdone, y.data()))) return rc;
+          if ((rc = K.pcapply(K.u, K.z))) return rc;
+          if ((rc = K.axpys(xd, 1.0, K.z, 1, &one))) return rc;
+        }
+      }
+      if (conv) { why = 2; break; }
+      if (its >= max_it) { why = -3; break; }
+    }
+  }
+  if (!on_device) {
+    CUDA_TRY(cudaMemcpyAsync(x, xd, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (its_out) *its_out = its;
+  if (reason) *reason = why;
+  if (rnorm_out) *rnorm_out = rn;
+  return 0;
+}
+
 int pflare_b200_get_stream(void *handle, void **stream) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
   *stream = (void *)c->stream;
@@ -2619,6 +2855,7 @@ void destroy_ctx(Ctx *c) {
     for (size_t p = 0; p < c->peer_arena.size(); ++p)
       if (c->peer_ipc[p] && c->peer_arena[p]) cudaIpcCloseMemHandle(c->peer_arena[p]);
     for (void *p : c->allocs) cudaFree(p);
+    if (c->ksp_hdots) cudaFreeHost(c->ksp_hdots);
     if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
   }

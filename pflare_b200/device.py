@@ -165,6 +165,36 @@ class DeviceAIR:
         check(self.L.pflare_b200_inv_apply(self.h, our_level, which, _ptr(x), _ptr(y), 0))
         return y
 
+    # ------------------------------------------------------------------ outer Krylov method (KSPSolve)
+    def ksp_set_operator(self, mat, offdiag=None, garray=None, cstart=0):
+        """System matrix of the outer solve (level-1 rows, natural numbering); call before finalize."""
+        ia, ja, a = _i32(mat.indptr), _i32(mat.indices), _f64(mat.data)
+        if offdiag is not None and garray is not None and len(garray) > 0:
+            oi, oj, oa = _i32(offdiag.indptr), _i32(offdiag.indices), _f64(offdiag.data)
+            ga = np.ascontiguousarray(garray, dtype=np.int64)
+            check(self.L.pflare_b200_ksp_set_operator(self.h, mat.shape[0], mat.shape[1], int(cstart), _ptr(ia), _ptr(ja), _ptr(a),
+                                                      ga.size, _ptr(oi), _ptr(oj), _ptr(oa), _ptr(ga)))
+        else:
+            check(self.L.pflare_b200_ksp_set_operator(self.h, mat.shape[0], mat.shape[1], int(cstart), _ptr(ia), _ptr(ja), _ptr(a),
+                                                      0, None, None, None, None))
+
+    def ksp_solve(self, b, x0, ksp_type="gmres", side="right", rtol=1e-5, atol=1e-50, max_it=10000, restart=30):
+        """KSPSolve on the device with host buffers: returns (x, its, converged, rnorm)."""
+        b = _f64(b)
+        x = np.array(x0, dtype=np.float64, copy=True)
+        its, why, rn = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
+        check(self.L.pflare_b200_ksp_solve(self.h, 0 if ksp_type == "gmres" else 1, 0 if side == "left" else 1, float(rtol), float(atol),
+                                           int(max_it), int(restart), _ptr(b), _ptr(x), 0, ctypes.byref(its), ctypes.byref(why),
+                                           ctypes.byref(rn)))
+        return x, its.value, why.value > 0, rn.value
+
+    def ksp_solve_ptr(self, b_ptr, x_ptr, ksp_type=0, side=1, rtol=1e-5, atol=1e-50, max_it=10000, restart=30):
+        its, why, rn = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
+        check(self.L.pflare_b200_ksp_solve(self.h, ksp_type, side, float(rtol), float(atol), int(max_it), int(restart),
+                                           ctypes.c_void_p(b_ptr), ctypes.c_void_p(x_ptr), 1, ctypes.byref(its), ctypes.byref(why),
+                                           ctypes.byref(rn)))
+        return its.value, why.value, rn.value
+
     def fc_smooth(self, our_level, b, x):
         b = _f64(b)
         x = np.array(x, dtype=np.float64, copy=True)

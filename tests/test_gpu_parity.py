@@ -154,6 +154,47 @@ def test_outer_gmres_iteration_counts(built_libs, name, rtol, side, bound):
     pc.destroy()
 
 
+@pytest.mark.parametrize("name,rtol,side,bound", [("adv1d_makefile", 1e-10, "right", 2), ("fd2d_25", 1e-5, "left", 5),
+                                                  ("fd3d_10_lump", 1e-10, "right", 4), ("fd2d_100_study", 1e-10, "right", 6),
+                                                  ("fd2d_full_mf", 1e-8, "right", 40)])
+def test_outer_krylov_on_device(built_libs, name, rtol, side, bound):
+    """KSPSolve on the device (pflare_b200_ksp_solve: GMRES(30) around the V-cycle, b = 0, x0 = 1 like the reference's drivers):
+    iteration count equal (+-1) to the host loop around the oracle and within the reference's -ksp_max_it bound, and the
+    solution solves the system."""
+    A, H = cases.build(name)
+    n = A.shape[0]
+    d = pflare_b200.DeviceAIR(H.no_levels)
+    d.ksp_set_operator(A)
+    hiergen.feed(H, d)
+    x, its_dev, conv, rn = d.ksp_solve(np.zeros(n), np.ones(n), ksp_type="gmres", side=side, rtol=rtol)
+    _, its_cpu, _ = gmres(A, np.zeros(n), np.ones(n), _oracle(H).apply, rtol=rtol, side=side)
+    assert conv and its_dev <= bound and abs(its_dev - its_cpu) <= 1, (its_dev, its_cpu)
+    if side == "right":
+        assert np.linalg.norm(A @ x) <= 10 * rtol * np.linalg.norm(A @ np.ones(n))
+    # a restart shorter than the iteration count exercises the restart path
+    x2, its2, conv2, _ = d.ksp_solve(np.zeros(n), np.ones(n), ksp_type="gmres", side=side, rtol=rtol, restart=2)
+    _, its2_cpu, _ = gmres(A, np.zeros(n), np.ones(n), _oracle(H).apply, rtol=rtol, side=side, restart=2)
+    assert conv2 and abs(its2 - its2_cpu) <= 1
+    d.close()
+
+
+def test_outer_richardson_on_device_pflareinv(built_libs):
+    """KSPRICHARDSON on the device around a PCPFLAREINV handle (tests/Makefile:548-553 style)."""
+    A, H = cases.build_inv("inv_arnoldi_asm")
+    n = A.shape[0]
+    b = cases.rhs(n)
+    d = pflare_b200.DeviceAIR(1)
+    d.ksp_set_operator(A)
+    hiergen.feed(H, d)
+    x, its, conv, rn = d.ksp_solve(b, np.zeros(n), ksp_type="richardson", rtol=1e-6, max_it=200)
+    O = _oracle(H)
+    _, its_cpu, conv_cpu = richardson(A, b, np.zeros(n), lambda v: O.inv_apply(1, oracle.INV_AFF, v), rtol=1e-6, max_it=200)
+    assert conv == conv_cpu and abs(its - its_cpu) <= 1
+    if conv:
+        assert np.linalg.norm(b - A @ x) <= 1e-5 * np.linalg.norm(b)
+    d.close()
+
+
 def test_edge_cases(built_libs):
     # zero rhs -> exactly zero; a single-level PCAIR is refused; wrong vector length is an error
     A, H = cases.build("fd2d_25")
