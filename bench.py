@@ -58,6 +58,12 @@ def make_problem(args):
         A = hiergen.adv_diff_fd(n, n, n)
         opts = hiergen.AirOptions(a_lump=True)
         name = "tests/adv_diff_fd.c 3D upwind advection %d^3, PCAIR -pc_air_a_lump" % n
+    elif w == "adv_diff_fd_3d_lair":
+        # BASELINE.json configs[3]: 3D FD, AIRG with lAIR Z (-pc_air_z_type lair, lair_distance 2), at the size that fits the budget
+        n = args.n
+        A = hiergen.adv_diff_fd(n, n, n, alpha=args.alpha)
+        opts = hiergen.AirOptions(a_lump=True, z_type="lair")
+        name = "tests/adv_diff_fd.c 3D advection-diffusion FD %d^3 (alpha %g), PCAIR -pc_air_z_type lair -pc_air_a_lump" % (n, args.alpha)
     elif w == "dg_upwind":
         n = args.n
         A = hiergen.dg_upwind_surrogate(n, n, 3)
@@ -86,7 +92,7 @@ def build_hierarchy(args):
     t = time.time()
     A, opts, name = make_problem(args)
     cd = None if args.no_cache else cache_dir()
-    path = os.path.join(cd, "%s_%d.npz" % (args.workload, args.n)) if cd else None
+    path = os.path.join(cd, "%s_%d_%g.npz" % (args.workload, args.n, args.alpha)) if cd else None
     if path and os.path.exists(path):
         try:
             H, _ = hio.load(path)
@@ -480,6 +486,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PFLARE_BENCH_WORKLOAD", "adv_diff_fd_2d"))
     ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("PFLARE_BENCH_N", "4096")))
+    ap.add_argument("--alpha", type=float, default=0.0, help="diffusion coefficient of the 3D workloads (0 = pure upwind advection)")
     ap.add_argument("--cpu-cycles", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check (development runs only)")

@@ -105,6 +105,16 @@ int pflare_b200_set_csr(void *handle, int our_level, int which, int m, int n_loc
                         const int *dj, const double *da, int n_ghost, const int *oi, const int *oj, const double *oa,
                         const int64_t *garray);
 
+/* PetscInt = 64-bit builds (--with-64-bit-indices; the reference's Makefile:75): the two upload calls above with 64-bit
+ * index arrays.  A rank's LOCAL block is narrowed to 32 bits on entry (rows, local columns and nonzeros of one rank
+ * must stay below 2^31 -- error 3 otherwise); global sizes are unrestricted (rstart, cstart and garray are 64-bit in
+ * both variants). */
+int pflare_b200_set_level_i64(void *handle, int our_level, int64_t rstart, int64_t n_local, int64_t n_fine, const int64_t *is_fine,
+                              int64_t n_coarse, const int64_t *is_coarse, const int64_t *smooth_order, int64_t n_smooth);
+int pflare_b200_set_csr_i64(void *handle, int our_level, int which, int64_t m, int64_t n_local_cols, int64_t cstart,
+                            const int64_t *di, const int64_t *dj, const double *da, int64_t n_ghost, const int64_t *oi,
+                            const int64_t *oj, const double *oa, const int64_t *garray);
+
 /* MATDIAGONAL inverse (Jacobi / weighted Jacobi / 0th-order sparsity polynomial):
  * MatMult = pointwise multiply by d (src/Weighted_Jacobi.F90:76-85). which = INV_AFF | INV_ACC. */
 int pflare_b200_set_diag(void *handle, int our_level, int which, int n, const double *d);

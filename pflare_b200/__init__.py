@@ -5,3 +5,4 @@ from ._capi import PflareB200Error, LIB_PATH, lib  # noqa: F401
 from .device import ClusterAIR, DeviceAIR, AFF, AFC, ACF, ACC, INV_AFF, INV_ACC, R, P, COARSE  # noqa: F401
 from .pc import PC, PCAIR, PCPFLAREINV  # noqa: F401
 from .upload import feed  # noqa: F401
+from . import petsc_io  # noqa: F401

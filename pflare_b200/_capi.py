@@ -24,6 +24,8 @@ SIGNATURES = {
     "pflare_b200_create": (c_int, [P(c_vp), c_int, c_int, c_vp, c_int, c_int]),
     "pflare_b200_set_level": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_int]),
     "pflare_b200_set_csr": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "pflare_b200_set_level_i64": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64]),
+    "pflare_b200_set_csr_i64": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "pflare_b200_set_diag": (c_int, [c_vp, c_int, c_int, c_int, c_vp]),
     "pflare_b200_set_poly": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int]),
     "pflare_b200_finalize_setup": (c_int, [c_vp]),

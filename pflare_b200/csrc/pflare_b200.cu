@@ -2296,6 +2296,38 @@ int pflare_b200_set_csr(void *handle, int our_level, int which, int m, int n_loc
   return set_csr_impl(c, our_level, which, m, n_local_cols, cstart, di, dj, da, n_ghost, oi, oj, oa, garray);
 }
 
+// ---- PetscInt = 64-bit builds (--with-64-bit-indices, Makefile:75 of the reference): the same two upload calls with
+// 64-bit index arrays.  A rank's LOCAL block is narrowed to 32 bits on entry (rows, local columns and nonzeros of one
+// rank must stay below 2^31; global sizes are unrestricted -- rstart / cstart / garray are 64-bit in both variants).
+static bool narrow(const int64_t *src, int64_t n, std::vector<int> *dst) {
+  dst->resize((size_t)std::max<int64_t>(n, 0));
+  for (int64_t i = 0; i < n; ++i) {
+    if (src[i] < 0 || src[i] > 2147483647LL) return false;
+    (*dst)[(size_t)i] = (int)src[i];
+  }
+  return true;
+}
+
+int pflare_b200_set_level_i64(void *handle, int our_level, int64_t rstart, int64_t n_local, int64_t n_fine, const int64_t *is_fine,
+                              int64_t n_coarse, const int64_t *is_coarse, const int64_t *smooth_order, int64_t n_smooth) {
+  if (n_local > 2147483647LL) return fail(3, "level %d: a rank's local block must have < 2^31 rows", our_level);
+  std::vector<int> f, cc, sm((size_t)std::max<int64_t>(n_smooth, 0));
+  if (!narrow(is_fine, n_fine, &f) || !narrow(is_coarse, n_coarse, &cc)) return fail(3, "level %d: local index out of the 32-bit range", our_level);
+  for (int64_t i = 0; i < n_smooth; ++i) sm[(size_t)i] = (int)smooth_order[i];
+  return pflare_b200_set_level(handle, our_level, rstart, (int)n_local, (int)n_fine, f.data(), (int)n_coarse, cc.data(), sm.data(), (int)n_smooth);
+}
+
+int pflare_b200_set_csr_i64(void *handle, int our_level, int which, int64_t m, int64_t n_local_cols, int64_t cstart, const int64_t *di,
+                            const int64_t *dj, const double *da, int64_t n_ghost, const int64_t *oi, const int64_t *oj, const double *oa,
+                            const int64_t *garray) {
+  if (m > 2147483647LL || n_local_cols > 2147483647LL || n_ghost > 2147483647LL) return fail(3, "a rank's local block must have < 2^31 rows / columns");
+  std::vector<int> i1, j1, i2, j2;
+  if (!narrow(di, m + 1, &i1) || !narrow(dj, di[m], &j1)) return fail(3, "operator %d of level %d: local block has >= 2^31 nonzeros or columns", which, our_level);
+  if (n_ghost > 0 && (!narrow(oi, m + 1, &i2) || !narrow(oj, oi[m], &j2))) return fail(3, "operator %d of level %d: off-diagonal block out of the 32-bit range", which, our_level);
+  return pflare_b200_set_csr(handle, our_level, which, (int)m, (int)n_local_cols, cstart, i1.data(), j1.data(), da, (int)n_ghost,
+                             n_ghost > 0 ? i2.data() : nullptr, n_ghost > 0 ? j2.data() : nullptr, oa, garray);
+}
+
 int pflare_b200_set_diag(void *handle, int our_level, int which, int n, const double *d) {
   Ctx *c; int rc = check_handle(handle, &c); if (rc) return rc;
   if (our_level < 1 || our_level > c->no_levels) return fail(2, "our_level %d out of range", our_level);

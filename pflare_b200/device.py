@@ -33,8 +33,9 @@ def _ptr(a):
 class DeviceAIR:
     """Handle to one uploaded hierarchy (``void *handle`` of include/pflare_b200.h)."""
 
-    def __init__(self, no_levels, rank=0, nranks=1, unique_id=None, device=0, _handle=None):
+    def __init__(self, no_levels, rank=0, nranks=1, unique_id=None, device=0, _handle=None, idx64=False):
         self.L = _capi.lib()
+        self.idx64 = bool(idx64)     # hand the index data over as 64-bit PetscInt (the *_i64 entry points)
         self.no_levels = int(no_levels)
         self.rank, self.nranks, self.device = rank, nranks, device
         self._owned = _handle is None
@@ -57,12 +58,27 @@ class DeviceAIR:
     def set_level(self, our_level, n, is_f, is_c, smooth_order, rstart=0):
         is_f, is_c, sm = _i32(is_f), _i32(is_c), _i32(smooth_order)
         self.n[our_level], self.nf[our_level], self.nc[our_level] = int(n), is_f.size, is_c.size
+        if self.idx64:
+            f8, c8, s8 = (np.ascontiguousarray(a, dtype=np.int64) for a in (is_f, is_c, sm))
+            check(self.L.pflare_b200_set_level_i64(self.h, our_level, int(rstart), int(n), f8.size, _ptr(f8), c8.size, _ptr(c8), _ptr(s8), s8.size))
+            return
         check(self.L.pflare_b200_set_level(self.h, our_level, int(rstart), int(n), is_f.size, _ptr(is_f), is_c.size,
                                            _ptr(is_c), _ptr(sm), sm.size))
 
     def set_csr(self, our_level, which, mat, offdiag=None, garray=None, cstart=0):
         """mat = diag block (scipy CSR, local columns); offdiag = CSR over compressed ghost columns."""
         ia, ja, a = _i32(mat.indptr), _i32(mat.indices), _f64(mat.data)
+        if self.idx64:
+            i8 = lambda v: np.ascontiguousarray(v, dtype=np.int64)
+            ia8, ja8 = i8(ia), i8(ja)
+            if offdiag is not None and garray is not None and len(garray) > 0:
+                oi8, oj8, oa, ga = i8(offdiag.indptr), i8(offdiag.indices), _f64(offdiag.data), i8(garray)
+                check(self.L.pflare_b200_set_csr_i64(self.h, our_level, which, mat.shape[0], mat.shape[1], int(cstart), _ptr(ia8), _ptr(ja8),
+                                                     _ptr(a), ga.size, _ptr(oi8), _ptr(oj8), _ptr(oa), _ptr(ga)))
+            else:
+                check(self.L.pflare_b200_set_csr_i64(self.h, our_level, which, mat.shape[0], mat.shape[1], int(cstart), _ptr(ia8), _ptr(ja8),
+                                                     _ptr(a), 0, None, None, None, None))
+            return
         if offdiag is not None and garray is not None and len(garray) > 0:
             oi, oj, oa = _i32(offdiag.indptr), _i32(offdiag.indices), _f64(offdiag.data)
             ga = np.ascontiguousarray(garray, dtype=np.int64)

@@ -3,6 +3,8 @@
 
   * <case>.npz          : a whole hierarchy (every operator the upload hook hands over), the seeded
                           rhs and the oracle's PCApply output, for the cases in tests/cases.py:GOLDEN.
+  * <case>.petsc        : the same container as PETSc binary objects (pflare_b200/petsc_io.py), the format a PFLARE build
+                          dumps through shim/pflare_b200_petsc.c; holds b and the oracle's x as the trailing Vec pair.
   * ilu_mat_stream.npz  : BASELINE.json configs[4] -- L and U from the ParILU(0) sweep of
                           /root/reference/tests/ilu_factors.c:484-567 on the reference's own fixture
                           /root/reference/tests/data/mat_stream_2364 (PETSc binary), the Newton-basis
@@ -36,6 +38,14 @@ def main():
         x = O.apply(b)
         hio.save(os.path.join(HERE, name + ".npz"), H, b=b, x_oracle=x)
         print(name, A.shape[0], H.no_levels, os.path.getsize(os.path.join(HERE, name + ".npz")))
+    # the same container in PETSc binary (pflare_b200/petsc_io.py: what a PFLARE build would dump), incl. a full-smoothing case
+    from pflare_b200 import petsc_io
+    for name in ("fd2d_25", "fd2d_full_mf"):
+        A, H = cases.build(name)
+        O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))
+        b = cases.rhs(A.shape[0])
+        petsc_io.save_hierarchy(os.path.join(HERE, name + ".petsc"), H, b, O.apply(b))
+        print(name + ".petsc", os.path.getsize(os.path.join(HERE, name + ".petsc")))
     ref = "/root/reference/tests/data/mat_stream_2364"
     mats, _ = hiergen.read_petsc_binary(ref)
     L, U, idu, sweeps = hiergen.parilu_factors(mats[0])

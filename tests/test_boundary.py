@@ -163,3 +163,55 @@ def test_warp_tile_format_and_row_sum_algorithm(tmp_path):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-o", exe, os.path.join(ROOT, "tests", "c", name + ".cpp")])
         out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and ok in out.stdout, out.stdout + out.stderr
+
+
+def test_petsc_binary_hierarchy_container_round_trip(built_libs, tmp_path):
+    """The PETSc-binary hierarchy container (pflare_b200/petsc_io.py): write -> read is bit exact, the
+    committed fixtures reproduce their stored PCApply output on the oracle, and the reader's primitives parse the
+    reference's own PETSc fixture tests/data/mat_stream_2364 (as committed under tests/golden/ilu_mat_stream.npz)."""
+    import numpy as np
+    import cases
+    import hiergen
+    import oracle
+    from pflare_b200 import petsc_io
+    from pflare_b200.upload import feed
+    for name in ("fd2d_fcf", "fd2d_mf_newton", "fd2d_full", "fd2d_jacobi"):
+        A, H = cases.build(name)
+        b = cases.rhs(A.shape[0])
+        xo = hiergen.feed(H, oracle.OracleAIR(H.no_levels)).apply(b)
+        path = str(tmp_path / (name + ".petsc"))
+        petsc_io.save_hierarchy(path, H, b, xo)
+        H2 = petsc_io.load_hierarchy(path)
+        assert H2.no_levels == H.no_levels and H2.options.full_smoothing_up_and_down == H.options.full_smoothing_up_and_down
+        for l1, l2 in zip(H.levels, H2.levels):
+            assert np.array_equal(l1.is_fine, l2.is_fine) and np.array_equal(l1.is_coarse, l2.is_coarse)
+            assert (l1.R != l2.R).nnz == 0 and (l1.P != l2.P).nnz == 0
+        x2 = feed(H2, oracle.OracleAIR(H2.no_levels)).apply(H2.b)
+        assert np.array_equal(x2, H2.x) and np.array_equal(x2, xo)
+    gold = os.path.join(ROOT, "tests", "golden")
+    for name in ("fd2d_25", "fd2d_full_mf"):
+        Hg = petsc_io.load_hierarchy(os.path.join(gold, name + ".petsc"))
+        xg = feed(Hg, oracle.OracleAIR(Hg.no_levels)).apply(Hg.b)
+        assert np.linalg.norm(xg - Hg.x) <= 1e-13 * np.linalg.norm(Hg.x)
+    with pytest.raises(ValueError):
+        petsc_io.load_hierarchy(os.path.join(gold, "fd2d_25.npz"))
+
+
+def test_64bit_petscint_upload_entry_points(built_libs):
+    """PetscInt = 64-bit builds: the *_i64 upload calls narrow a rank's local block to 32 bits and refuse anything that does
+    not fit (host-only planning context: no GPU needed)."""
+    import numpy as np
+    A, H = cases.build("fd2d_fcf")
+    d32 = pflare_b200.DeviceAIR(H.no_levels, device=-1)
+    d64 = pflare_b200.DeviceAIR(H.no_levels, device=-1, idx64=True)
+    hiergen.feed(H, d32)
+    hiergen.feed(H, d64)
+    for l, lv in enumerate(H.levels, start=1):
+        assert np.array_equal(d64.get_is(l, 0), lv.is_fine) and np.array_equal(d64.get_is(l, 1), lv.is_coarse)
+    assert d32.stats()["nnz_per_cycle"] == d64.stats()["nnz_per_cycle"] and d32.stats()["algorithmic_bytes"] == d64.stats()["algorithmic_bytes"]
+    # an index beyond 2^31 is refused loudly
+    bad = np.array([0, 1, 2 ** 31 + 5], dtype=np.int64)
+    L = pflare_b200.lib()
+    rc = L.pflare_b200_set_level_i64(d64.h, 1, 0, 3, 3, ctypes.c_void_p(bad.ctypes.data), 0, None, None, 0)
+    assert rc == 3 and b"32-bit" in L.pflare_b200_last_error()
+    d32.close(); d64.close()

@@ -87,6 +87,16 @@ def test_golden_fixtures(built_libs, name):
     d.close()
 
 
+@pytest.mark.parametrize("name", ["fd2d_25", "fd2d_full_mf"])
+def test_golden_petsc_binary_container(built_libs, name):
+    """A hierarchy handed over as PETSc binary objects (the container a PFLARE build dumps, pflare_b200/petsc_io.py)."""
+    from pflare_b200 import petsc_io
+    H = petsc_io.load_hierarchy(os.path.join(GOLD, name + ".petsc"))
+    pc = pflare_b200.PC().setType("air").setHierarchy(H)
+    assert cases.rel_l2(pc.apply(H.b), H.x) <= TOL
+    pc.destroy()
+
+
 def test_golden_ilu_factors_pflareinv_newton(built_libs):
     """configs[4]: PCPFLAREINV Newton-basis polynomial (matrix-free) on the ParILU factors of the reference's
     own fixture tests/data/mat_stream_2364."""
@@ -130,6 +140,16 @@ def test_level_smoother_and_inverse_parity(built_libs, name):
         if lv.inv_A_cc is not None:
             v = cases.rhs(lv.is_coarse.size, seed=300 + l)
             assert cases.rel_l2(d.inv_apply(l, pflare_b200.INV_ACC, v), O.inv_apply(l, oracle.INV_ACC, v)) <= TOL
+    d.close()
+
+
+def test_64bit_petscint_upload(built_libs):
+    """The *_i64 upload entry points (PetscInt = 64-bit builds) give the same V-cycle."""
+    A, H = cases.build("fd2d_fcf")
+    b = cases.rhs(A.shape[0])
+    d = pflare_b200.DeviceAIR(H.no_levels, idx64=True)
+    hiergen.feed(H, d)
+    assert cases.rel_l2(d.apply(b), _oracle(H).apply(b)) <= TOL
     d.close()
 
 
