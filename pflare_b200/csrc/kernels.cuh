@@ -670,8 +670,8 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wc_kernel(const SpmvOp op) {
 // ring and ~80 registers, 24 warps per SM are resident (the TMA-ring engine: 16) and the whole L1
 // serves the gathers: latency is hidden by occupancy instead of by a software pipeline.
 __device__ __forceinline__ int ld_stream_nc(const int *p) { return __ldcs(p); }
-template <int EPI, int KP, bool GHOST>
-__global__ void __launch_bounds__(256, 3) spmv_sv_kernel(const SpmvOp op) {
+template <int EPI, int KP, bool GHOST, int MINB>
+__global__ void __launch_bounds__(256, MINB) spmv_sv_kernel(const SpmvOp op) {
   typedef EpiT<EPI> E;
   typedef typename E::Pre Pre;
   constexpr bool XW = E::kXw;

@@ -223,6 +223,7 @@ struct Ctx {
   int wt_format = 0;     // kernel 2 operator storage: 0 = by mean row length (fmt_split), 1 = chunk format, 2 = row-aligned lanes
   double fmt_split = 8.0;   // measured on the 4096^2 cycle: 3 -> 2.82 ms, 4.5 -> 2.65 ms, 8 -> 2.62 ms
   int engine = 1;        // kernel 2 (row-aligned format): 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
+  int sv_minb = 4;       // direct engine: resident CTAs per SM it is compiled for (3: 80 registers, 4: 64, 5: 48); measured 2.62 / 2.56 ms at 3 / 4
   int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
@@ -788,12 +789,20 @@ struct SharedComm {
   std::vector<const int64_t *> a_send;
   struct V { const char *sbuf; const int64_t *scnt, *sdsp; };
   std::vector<V> v_send;
+  bool aborted = false;   // a rank failed: every barrier returns at once (no rank is left waiting for it)
   explicit SharedComm(int p) : P(p), a_send(p), v_send(p) {}
-  void barrier() {
+  bool barrier() {
     std::unique_lock<std::mutex> lk(mu);
+    if (aborted) return false;
     const int gen = generation;
     if (++arrived == P) { arrived = 0; ++generation; cv.notify_all(); }
-    else cv.wait(lk, [&] { return gen != generation; });
+    else cv.wait(lk, [&] { return gen != generation || aborted; });
+    return !aborted;
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(mu);
+    aborted = true;
+    cv.notify_all();
   }
 };
 struct SharedRankComm : HostComm {
@@ -802,23 +811,25 @@ struct SharedRankComm : HostComm {
   SharedRankComm(std::shared_ptr<SharedComm> s, int rank) : sc(s), r(rank) {}
   int rank() const override { return r; }
   int size() const override { return sc->P; }
-  int alltoall(const int64_t *send, int64_t *recv, std::string *) override {
+  int alltoall(const int64_t *send, int64_t *recv, std::string *err) override {
     sc->a_send[r] = send;
-    sc->barrier();
+    if (!sc->barrier()) { if (err) *err = "another rank of the group failed"; return 1; }
     for (int p = 0; p < sc->P; ++p) recv[p] = sc->a_send[p][r];
-    sc->barrier();
+    if (!sc->barrier()) { if (err) *err = "another rank of the group failed"; return 1; }
     return 0;
   }
   int alltoallv(const char *sbuf, const int64_t *scnt, const int64_t *sdsp, char *rbuf, const int64_t *rcnt, const int64_t *rdsp,
-                std::string *) override {
+                std::string *err) override {
     sc->v_send[r] = {sbuf, scnt, sdsp};
-    sc->barrier();
+    if (!sc->barrier()) { if (err) *err = "another rank of the group failed"; return 1; }
+    int bad = 0;
     for (int p = 0; p < sc->P; ++p) {
       const SharedComm::V &v = sc->v_send[p];
-      if (rcnt[p] != v.scnt[r]) return 1;
+      if (rcnt[p] != v.scnt[r]) { bad = 1; continue; }
       if (rcnt[p]) memcpy(rbuf + rdsp[p], v.sbuf + v.sdsp[r], (size_t)rcnt[p]);
     }
-    sc->barrier();
+    if (bad) { sc->abort(); if (err) *err = "receive counts disagree with the senders'"; return 1; }
+    if (!sc->barrier()) { if (err) *err = "another rank of the group failed"; return 1; }
     return 0;
   }
 };
@@ -921,9 +932,9 @@ int launch_wt_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   return 0;
 }
 // direct engine (no shared memory): one instantiation per (epilogue class, slots per lane, ghost columns)
-template <int EPI, int KP, bool GH>
+template <int EPI, int KP, bool GH, int MINB>
 int launch_sv_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_sv_kernel<EPI, KP, GH>;
+  auto kern = spmv_sv_kernel<EPI, KP, GH, MINB>;
   static int per_sm = 0;
   int rc = kernel_per_sm(kern, 256, 0, &per_sm);
   if (rc || dry) return rc;
@@ -949,7 +960,9 @@ template <int EPI, int KP>
 int launch_wt_kp(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   const bool gh = s.xg != nullptr;
   if (c->engine == 2) return gh ? launch_thin_inst<EPI, KP, true>(c, s, st, dry) : launch_thin_inst<EPI, KP, false>(c, s, st, dry);
-  if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true>(c, s, st, dry) : launch_sv_inst<EPI, KP, false>(c, s, st, dry);
+  if (c->engine == 1 && c->sv_minb == 5) return gh ? launch_sv_inst<EPI, KP, true, 5>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 5>(c, s, st, dry);
+  if (c->engine == 1 && c->sv_minb == 4) return gh ? launch_sv_inst<EPI, KP, true, 4>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 4>(c, s, st, dry);
+  if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true, 3>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 3>(c, s, st, dry);
   if (c->wt_stages == 3) return gh ? launch_wt_inst<EPI, KP, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 3>(c, s, st, dry);
   return gh ? launch_wt_inst<EPI, KP, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 2>(c, s, st, dry);
 }
@@ -1500,7 +1513,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
   ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->full_smooth = c->full_smooth; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
-  ch->kernel = c->kernel; ch->wt_format = c->wt_format; ch->fmt_split = c->fmt_split; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+  ch->kernel = c->kernel; ch->wt_format = c->wt_format; ch->fmt_split = c->fmt_split; ch->engine = c->engine; ch->sv_minb = c->sv_minb; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
   for (int l = LA; l <= NL; ++l) {
@@ -2820,6 +2833,10 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
     if (value != 0 && value != 1 && value != 2) return fail(2, "engine must be 0 (TMA ring), 1 (direct) or 2 (thin warps)");
     c->engine = (int)value;
   }
+  else if (k == "sv_minb") {
+    if (value != 3 && value != 4 && value != 5) return fail(2, "sv_minb must be 3, 4 or 5");
+    c->sv_minb = (int)value;
+  }
   else if (k == "wt_stages") {
     if (value != 2 && value != 3) return fail(2, "wt_stages must be 2 or 3");
     c->wt_stages = (int)value;
@@ -2849,7 +2866,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
     Ctx *ch = c->child.get();
-    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->sv_minb = c->sv_minb; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
     ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   }
   return 0;
@@ -2963,9 +2980,13 @@ int pflare_b200_cluster_finalize(void *cluster) {
       Ctx *c = cl->ranks[(size_t)r].get();
       if (c->device >= 0) cudaSetDevice(c->device);
       rcs[(size_t)r] = finalize_ctx(c);
-      if (rcs[(size_t)r]) errs[(size_t)r] = g_err;
+      if (rcs[(size_t)r]) { errs[(size_t)r] = g_err; cl->shared->abort(); }   // wake the ranks waiting in a setup collective
     });
   for (auto &t : th) t.join();
+  cl->shared->aborted = false;   // a later, corrected finalize may run again
+  cl->shared->arrived = 0;
+  for (int r = 0; r < P; ++r)
+    if (rcs[(size_t)r] && errs[(size_t)r].find("another rank") == std::string::npos) return fail(rcs[(size_t)r], "rank %d: %s", r, errs[(size_t)r].c_str());
   for (int r = 0; r < P; ++r)
     if (rcs[(size_t)r]) return fail(rcs[(size_t)r], "rank %d: %s", r, errs[(size_t)r].c_str());
   cl->finalized = true;

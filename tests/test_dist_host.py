@@ -157,3 +157,18 @@ def test_gloo_two_processes(built_libs):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "GLOO_DIST_OK" in out.stdout
+
+
+def test_group_finalize_fails_instead_of_hanging_when_one_rank_is_incomplete(built_libs):
+    """A rank that returns early from finalize (level never set) must not leave the others blocked in a setup collective."""
+    A, H = cases.build("fd2d_25")
+    parts = hiergen.partition(H, 3)
+    cl = pflare_b200.ClusterAIR(H.no_levels, 3, device=-1)
+    for r, lh in enumerate(parts):
+        if r == 1:
+            continue            # rank 1 uploads nothing
+        lh.feed(cl.ranks[r])
+    with pytest.raises(pflare_b200.PflareB200Error) as e:
+        cl.finalize()
+    assert "rank 1" in str(e.value)
+    cl.close()
