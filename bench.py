@@ -418,10 +418,10 @@ def run_gpu(args):
     spmv_by = tot_by / reps
     achieved = spmv_by / (ms_dev * 1e-3) / 1e9
     per_launch = tot_by / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
-    kernel_id = {0: "spmv_stream_kernel", 1: "spmv_tma_kernel<256,1024,2>", 2: "spmv_wt_kernel"}[int(dict(kv.split("=") for kv in args.opt).get("kernel", 2))]
+    kernel_id = {0: "spmv_stream_kernel", 1: "spmv_tma_kernel<256,1024,2>", 2: "spmv_wc_kernel + spmv_sv_kernel"}[int(float(dict(kv.split("=") for kv in args.opt).get("kernel", 2)))]
     roof = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "kernel": kernel_id + " (CSR SpMV mega-op, all epilogue classes)",
+        "kernel": kernel_id + " (SpMV mega-op on warp-tile storage: chunk-format TMA-ring kernel for short rows, direct kernel on row-aligned lanes otherwise)",
         "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650",
         "how": "algorithmic bytes (SURVEY.md 8d) of all SpMV launches of one V-cycle / graph-mode cycle time (CUDA events on the library stream)",
         "achieved_per_launch_events": per_launch,

@@ -202,17 +202,25 @@ int pflare_b200_get_stats(void *handle, double *stats, int nstats);
 int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, int max_ops, float *ms, double *bytes,
                               int *level, int *kind, int *n_ops);
 
-/* Runtime switches: key "graph" (0/1), "tail_rows" / "tail_nnz" (levels with <= this many rows and
- * nonzeros per operator run in the single-CTA tail kernel), "fuse" (0/1 fused epilogues vs one kernel
- * per PETSc call), "kernel" (SpMV kernel variant; 0 = first-generation smem-staged kernel, 1.. =
- * TMA-pipelined variants; variants other than 0 must be chosen before finalize_setup), "ctas_per_sm",
- * "agg_rows" (multi-rank, before finalize_setup: levels with <= this many global rows are agglomerated
- * onto rank 0; 0 = never), "dense_rows" (levels with <= this many rows are collapsed into one dense
- * operator built from the same kernels at setup; 0 = off), "pdl" (programmatic dependent launch),
- * "overlap" (NCCL exchange on a side stream under the interior tiles), "p2p" (before finalize_setup:
- * peer-memory push exchange over CUDA IPC instead of NCCL), "wide_rows" / "wide_min_rows" (before
- * finalize_setup: operators with fewer nonzeros per row / at least that many rows use the wide-tile
- * kernel; off by default). */
+/* Switches.  Options of the reference that change the apply:
+ *   "full_smoothing_up_and_down" (before finalize_setup)  -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1), one
+ *                  Richardson sweep with inv_A_ff(level) on ALL unknowns down and up, residual restriction R (b - A x)
+ *                  (src/AIR_MG_Setup.F90:978-1074); the hook hands over coarse_matrix(level) + inv_A_ff(level) instead of A_ff / A_fc.
+ * Execution switches (results stay within the 1e-12 parity bar):
+ *   "graph" (0/1) CUDA graph of the cycle; "pdl" programmatic dependent launch; "fuse" (0: one kernel per PETSc call instead of
+ *   the fused epilogues); "epi_classes" (0: run-time branched epilogue instead of the compiled classes);
+ *   "kernel" (before finalize_setup) 0 = CSR stream kernel (also the fallback for rows longer than a warp tile), 1 = round-1 TMA
+ *                  kernel with CTA tiles (A/B baseline), 2 = warp-tile storage (default);
+ *   "wt_format" / "fmt_split" (before finalize_setup) warp-tile storage per operator: 0 = by mean row length (< fmt_split, default 8:
+ *                  chunk format, else row-aligned lanes), 1 / 2 = force one of them;
+ *   "engine" kernel of the row-aligned storage: 0 = TMA ring, 1 = direct (default), 2 = thin warps; "sv_minb" resident CTAs per SM the
+ *                  direct engine is compiled for (3, 4 default, 5); "wt_stages" ring depth of the TMA engines (2 default, 3);
+ *   "ctas_per_sm" / "max_ctas" caps on the persistent grids (tests: many tiles per warp);
+ *   "dense_rows" levels with <= this many rows are collapsed into one dense operator built from the same kernels at setup (0 = off);
+ *   "fuse_perm" (before finalize_setup) 0 (default) / 1 / 2: entry / exit permutation fused into the level-1 ops (measured slower);
+ *   "agg_rows" (multi-rank, before finalize_setup) levels with <= this many global rows are agglomerated onto rank 0 (0 = never);
+ *   "overlap" NCCL exchange on a side stream under the interior tiles; "p2p" (before finalize_setup) peer-memory push exchange over
+ *                  CUDA IPC instead of NCCL. */
 int pflare_b200_set_option(void *handle, const char *key, double value);
 
 const char *pflare_b200_last_error(void);

@@ -1708,7 +1708,11 @@ int finalize_ctx(Ctx *c) {
   c->plans.clear();
   // sizes must chain locally: n_{l+1} == n_coarse(l)
   for (int l = 1; l < NL; ++l)
-    if (c->L[l + 1].n != c->L[l].nc) return fail(2, "level %d has %d rows but level %d has %d C points", l + 1, c->L[l + 1].n, l, c->L[l].nc);
+    if (c->L[l + 1].n != c->L[l].nc)
+      return fail(2, "level %d has %d rows but level %d has %d C points on this rank: the library keeps PETSc's ownership on every level "
+                     "(x_c of level l is x of level l+1); hierarchies repartitioned by -pc_air_processor_agglom are not accepted -- run the "
+                     "reference's setup with -pc_air_processor_agglom 0 (the library agglomerates its coarse levels itself, option agg_rows)",
+                  l + 1, c->L[l + 1].n, l, c->L[l].nc);
 
   // ---- X1: ownership ranges of every level + the structural flags that shape the program
   std::vector<int64_t> onept((size_t)NL + 1, 1), affdiag((size_t)NL + 1, 1);

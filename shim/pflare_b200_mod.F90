@@ -21,9 +21,9 @@ module pflare_b200_mod
                                 B200_INV_ACC = 5, B200_R = 6, B200_P = 7, B200_COARSE = 8
 
    interface
-      subroutine pflare_b200_create_c(handle, A_top, no_levels) bind(c, name="pflare_b200_create_c")
+      subroutine pflare_b200_create_c(handle, aux, A_top, no_levels) bind(c, name="pflare_b200_create_c")
          use iso_c_binding
-         type(c_ptr) :: handle
+         type(c_ptr) :: handle, aux                    ! aux: per-PC communicator slot + ordering events (air_data%b200_aux)
          integer(c_long_long) :: A_top
          integer(c_long_long), value :: no_levels      ! PetscInt
       end subroutine
@@ -62,15 +62,22 @@ module pflare_b200_mod
          use iso_c_binding
          type(c_ptr) :: handle
       end subroutine
-      subroutine pflare_b200_apply_c(handle, x, y) bind(c, name="pflare_b200_apply_c")
+      subroutine pflare_b200_apply_c(handle, aux, x, y) bind(c, name="pflare_b200_apply_c")
          use iso_c_binding
-         type(c_ptr) :: handle
+         type(c_ptr) :: handle, aux
          integer(c_long_long) :: x, y
       end subroutine
-      subroutine pflare_b200_destroy_c(handle) bind(c, name="pflare_b200_destroy_c")
+      subroutine pflare_b200_destroy_c(handle, aux) bind(c, name="pflare_b200_destroy_c")
          use iso_c_binding
-         type(c_ptr) :: handle
+         type(c_ptr) :: handle, aux
       end subroutine
+      function pflare_b200_set_option(handle, key, val) bind(c, name="pflare_b200_set_option")
+         use iso_c_binding
+         type(c_ptr), value :: handle
+         character(kind=c_char), dimension(*) :: key
+         real(c_double), value :: val
+         integer(c_int) :: pflare_b200_set_option
+      end function
    end interface
 
    contains
@@ -115,12 +122,25 @@ module pflare_b200_mod
       type(air_multigrid_data), intent(inout) :: air_data
       type(tMat), intent(in)                  :: amat
 
-      integer :: our_level, no_levels
+      integer :: our_level, no_levels, ierr_abort
+      integer(c_int) :: ierr_c
       logical :: any_c
       type(tMat) :: level_mat
 
       no_levels = air_data%no_levels
-      call pflare_b200_create_c(air_data%b200_handle, amat%v, int(no_levels, c_long_long))
+      ! The library keeps PETSc's ownership on every level (x_c of level l IS x of level l+1 on the same rank).  Levels
+      ! that the reference repartitions onto fewer ranks (-pc_air_processor_agglom, default .TRUE.,
+      ! src/AIR_Data_Type.F90:64, src/AIR_MG_Setup.F90:645-907) break that: run with -pc_air_processor_agglom 0 and let
+      ! the library agglomerate its coarse levels itself (option "agg_rows"); finalize_setup fails loudly otherwise
+      ! ("level l+1 has X rows but level l has Y C points").
+      if (air_data%options%processor_agglom) then
+         print *, "pflare_b200: -pc_air_processor_agglom must be 0 (the library agglomerates coarse levels itself)"
+         call MPI_Abort(MPI_COMM_WORLD, MPI_ERR_OTHER, ierr_abort)
+      end if
+      call pflare_b200_create_c(air_data%b200_handle, air_data%b200_aux, amat%v, int(no_levels, c_long_long))
+      if (air_data%options%full_smoothing_up_and_down) then
+         ierr_c = pflare_b200_set_option(air_data%b200_handle, "full_smoothing_up_and_down"//c_null_char, 1d0)
+      end if
       do our_level = 1, no_levels - 1
          ! the level operator fixes the row ownership of the level: level 1 = amat, else coarse_matrix(our_level)
          level_mat = amat
@@ -129,13 +149,18 @@ module pflare_b200_mod
                   air_data%IS_fine_index(our_level)%v, air_data%IS_coarse_index(our_level)%v, &
                   int(air_data%smooth_order_levels(our_level)%array, c_int), &
                   int(size(air_data%smooth_order_levels(our_level)%array), c_int))
-         call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_AFF, air_data%A_ff(our_level)%v)
-         call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_AFC, air_data%A_fc(our_level)%v)
+         if (air_data%options%full_smoothing_up_and_down) then
+            ! the smoother inverts the whole level matrix (src/AIR_MG_Setup.F90:1014-1024): hand over coarse_matrix(level)
+            call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_COARSE, level_mat%v)
+         else
+            call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_AFF, air_data%A_ff(our_level)%v)
+            call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_AFC, air_data%A_fc(our_level)%v)
+         end if
          call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_R, air_data%restrictors(our_level)%v)
          call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_P, air_data%prolongators(our_level)%v)
          call upload_inverse_b200(air_data%b200_handle, our_level, B200_INV_AFF, air_data%inv_A_ff(our_level), &
                   air_data%options%inverse_type, air_data%options%diag_scale_polys)
-         any_c = any(air_data%smooth_order_levels(our_level)%array < 0)
+         any_c = any(air_data%smooth_order_levels(our_level)%array < 0) .AND. .NOT. air_data%options%full_smoothing_up_and_down
          if (any_c) then
             call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_ACF, air_data%A_cf(our_level)%v)
             call pflare_b200_upload_mat_c(air_data%b200_handle, int(our_level, c_long_long), B200_ACC, air_data%A_cc(our_level)%v)
@@ -158,15 +183,16 @@ module pflare_b200_mod
       type(tVec), intent(in)    :: x
       type(tVec), intent(inout) :: y
       PetscErrorCode, intent(out) :: ierr
-      call pflare_b200_apply_c(air_data%b200_handle, x%v, y%v)
+      call pflare_b200_apply_c(air_data%b200_handle, air_data%b200_aux, x%v, y%v)
       ierr = 0          ! Fortran PETSc callbacks must set ierr (src/FC_Smooth.F90:492-493)
    end subroutine apply_air_b200
 
    ! Call from reset_air_data (src/AIR_Data_Type_Routines.F90:105)
    subroutine destroy_air_b200(air_data)
       type(air_multigrid_data), intent(inout) :: air_data
-      if (c_associated(air_data%b200_handle)) call pflare_b200_destroy_c(air_data%b200_handle)
+      if (c_associated(air_data%b200_handle)) call pflare_b200_destroy_c(air_data%b200_handle, air_data%b200_aux)
       air_data%b200_handle = c_null_ptr
+      air_data%b200_aux = c_null_ptr
    end subroutine destroy_air_b200
 
 end module pflare_b200_mod

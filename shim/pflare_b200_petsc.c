@@ -36,12 +36,18 @@ static int b200_alltoallv(void *ctx, const char *sbuf, const int64_t *scnt, cons
   return rc != MPI_SUCCESS;
 }
 
-/* One static communicator slot per handle would live in air_data; shown here for a single PC. */
-static MPI_Comm b200_comm;
+/* Per-PC state kept next to the library handle in air_data (two c_ptr members: b200_handle, b200_aux): every PCAIR /
+ * PCPFLAREINV instance owns its own communicator slot and ordering events (per-instance handle rule,
+ * src/AIR_Data_Type.F90:344-349; regression tests/ex6_two_airg.c). */
+typedef struct {
+  MPI_Comm    comm;          /* the PC's communicator: setup-time exchanges of the library */
+  cudaEvent_t ev_in, ev_out; /* ordering between PETSc's stream and the library's stream */
+} B200Aux;
 
-PETSC_INTERN void pflare_b200_create_c(void **handle, Mat *A_top, PetscInt no_levels)
+PETSC_INTERN void pflare_b200_create_c(void **handle, void **aux_out, Mat *A_top, PetscInt no_levels)
 {
   MPI_Comm    comm;
+  B200Aux    *aux;
   PetscMPIInt rank, size;
   int         device = 0, ndev = 1;
   char        uid[PFLARE_B200_UNIQUE_ID_BYTES];
@@ -57,10 +63,12 @@ PETSC_INTERN void pflare_b200_create_c(void **handle, Mat *A_top, PetscInt no_le
     PetscCallMPIAbort(comm, MPI_Bcast(uid, PFLARE_B200_UNIQUE_ID_BYTES, MPI_BYTE, 0, comm));
   }
   B200_CHECK(pflare_b200_create(handle, rank, size, size > 1 ? uid : NULL, device, (int)no_levels));
-  if (size > 1) {
-    b200_comm = comm;
-    B200_CHECK(pflare_b200_set_host_exchange(*handle, (void *)b200_alltoall, (void *)b200_alltoallv, &b200_comm));
-  }
+  PetscCallVoid(PetscNew(&aux));
+  aux->comm = comm;
+  cudaEventCreateWithFlags(&aux->ev_in, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&aux->ev_out, cudaEventDisableTiming);
+  *aux_out = aux;
+  if (size > 1) B200_CHECK(pflare_b200_set_host_exchange(*handle, (void *)b200_alltoall, (void *)b200_alltoallv, &aux->comm));
 }
 
 /* IS_fine_index / IS_coarse_index (global, sorted) -> local lists; smooth_order = smooth_order_levels(l)%array */
@@ -107,9 +115,14 @@ PETSC_INTERN void pflare_b200_upload_mat_c(void **handle, PetscInt our_level, in
     PetscCallVoid(PetscMalloc1(ng, &g64));
     for (PetscInt k = 0; k < ng; ++k) g64[k] = (int64_t)garray[k];
   }
-  /* PetscInt must be 32-bit (the only configuration the reference's load tests cover, Makefile:84-86) */
+#if defined(PETSC_USE_64BIT_INDICES)
+  /* --with-64-bit-indices (Makefile:75): the _i64 entry point narrows this rank's local block (must stay below 2^31) */
+  B200_CHECK(pflare_b200_set_csr_i64(*handle, (int)our_level, which, m, n, (int64_t)cstart, (const int64_t *)di, (const int64_t *)dj, da, ng,
+                                     (const int64_t *)oi, (const int64_t *)oj, oa, g64));
+#else
   B200_CHECK(pflare_b200_set_csr(*handle, (int)our_level, which, (int)m, (int)n, (int64_t)cstart, (const int *)di, (const int *)dj,
                                  da, (int)ng, (const int *)oi, (const int *)oj, oa, g64));
+#endif
   PetscCallVoid(MatSeqAIJRestoreArrayRead(Ad, &da));
   PetscCallVoid(MatRestoreRowIJ(Ad, 0, PETSC_FALSE, PETSC_FALSE, &nd, &di, &dj, &done));
   if (Ao) {
@@ -134,35 +147,105 @@ PETSC_INTERN void pflare_b200_upload_diag_c(void **handle, PetscInt our_level, i
   PetscCallVoid(VecDestroy(&d));
 }
 
+/* Stream ordering around a device-pointer call.  The library runs on its own non-blocking stream
+ * (pflare_b200_get_stream); PETSc's kernels that produced x run on the PetscDeviceContext's stream.  BEFORE the call
+ * the library stream waits for PETSc's stream, AFTER it PETSc's stream waits for the library's: no host
+ * synchronisation, and a device KSP never reads a half-written vector. */
+static void b200_order_in(void *handle, B200Aux *aux, cudaStream_t *petsc_stream)
+{
+  PetscDeviceContext dctx;
+  void              *hdl = NULL, *lib = NULL;
+  PetscCallVoid(PetscDeviceContextGetCurrentContext(&dctx));
+  PetscCallVoid(PetscDeviceContextGetStreamHandle(dctx, &hdl));
+  *petsc_stream = *(cudaStream_t *)hdl;
+  B200_CHECK(pflare_b200_get_stream(handle, &lib));
+  cudaEventRecord(aux->ev_in, *petsc_stream);
+  cudaStreamWaitEvent((cudaStream_t)lib, aux->ev_in, 0);
+}
+static void b200_order_out(void *handle, B200Aux *aux, cudaStream_t petsc_stream)
+{
+  void *lib = NULL;
+  B200_CHECK(pflare_b200_get_stream(handle, &lib));
+  cudaEventRecord(aux->ev_out, (cudaStream_t)lib);
+  cudaStreamWaitEvent(petsc_stream, aux->ev_out, 0);
+}
+
+/* x (read) and y (write) either both on the device or both on the host: a mixed pair is brought to the host (PETSc
+ * synchronises and copies inside VecGetArray*), never passed with the wrong pointer kind */
+static int b200_get_arrays(Vec x, Vec y, const PetscScalar **xa, PetscScalar **ya)
+{
+  PetscMemType mx, my;
+  PetscCallAbort(PETSC_COMM_SELF, VecGetArrayReadAndMemType(x, xa, &mx));
+  PetscCallAbort(PETSC_COMM_SELF, VecGetArrayWriteAndMemType(y, ya, &my));
+  if (PetscMemTypeDevice(mx) && PetscMemTypeDevice(my)) return 1;
+  if (PetscMemTypeHost(mx) && PetscMemTypeHost(my)) return 0;
+  PetscCallAbort(PETSC_COMM_SELF, VecRestoreArrayReadAndMemType(x, xa));
+  PetscCallAbort(PETSC_COMM_SELF, VecRestoreArrayWriteAndMemType(y, ya));
+  PetscCallAbort(PETSC_COMM_SELF, VecGetArrayRead(x, xa));   /* host copies */
+  PetscCallAbort(PETSC_COMM_SELF, VecGetArrayWrite(y, ya));
+  return 2;
+}
+static void b200_restore_arrays(Vec x, Vec y, int kind, const PetscScalar **xa, PetscScalar **ya)
+{
+  if (kind == 2) {
+    PetscCallVoid(VecRestoreArrayRead(x, xa));
+    PetscCallVoid(VecRestoreArrayWrite(y, ya));
+  } else {
+    PetscCallVoid(VecRestoreArrayReadAndMemType(x, xa));
+    PetscCallVoid(VecRestoreArrayWriteAndMemType(y, ya));
+  }
+}
+
 /* PCApply: x, y are the Vecs of PCApply_AIR_Shell (src/PCAIR_Shell.F90:170-188) */
-PETSC_INTERN void pflare_b200_apply_c(void **handle, Vec *x, Vec *y)
+PETSC_INTERN void pflare_b200_apply_c(void **handle, void **aux_p, Vec *x, Vec *y)
 {
   const PetscScalar *xa;
   PetscScalar       *ya;
-  PetscMemType       mx, my;
-  PetscCallVoid(VecGetArrayReadAndMemType(*x, &xa, &mx));
-  PetscCallVoid(VecGetArrayWriteAndMemType(*y, &ya, &my));
-  const int on_device = PetscMemTypeDevice(mx) && PetscMemTypeDevice(my);
-  B200_CHECK(pflare_b200_apply(*handle, xa, ya, on_device));
-  if (on_device) B200_CHECK(pflare_b200_synchronize(*handle)); /* or order the library stream with PETSc's device context */
-  PetscCallVoid(VecRestoreArrayReadAndMemType(*x, &xa));
-  PetscCallVoid(VecRestoreArrayWriteAndMemType(*y, &ya));
+  cudaStream_t       ps = NULL;
+  B200Aux           *aux = (B200Aux *)*aux_p;
+  const int          kind = b200_get_arrays(*x, *y, &xa, &ya);
+  if (kind == 1) b200_order_in(*handle, aux, &ps);
+  B200_CHECK(pflare_b200_apply(*handle, xa, ya, kind == 1));
+  if (kind == 1) b200_order_out(*handle, aux, ps);
+  b200_restore_arrays(*x, *y, kind, &xa, &ya);
 }
 
 /* PCPFLAREINV: y = mat_inverse * x (src/PCPFLAREINV.c:618-626) */
-PETSC_INTERN void pflare_b200_inv_apply_c(void **handle, Vec *x, Vec *y)
+PETSC_INTERN void pflare_b200_inv_apply_c(void **handle, void **aux_p, Vec *x, Vec *y)
 {
   const PetscScalar *xa;
   PetscScalar       *ya;
-  PetscMemType       mx, my;
-  PetscCallVoid(VecGetArrayReadAndMemType(*x, &xa, &mx));
-  PetscCallVoid(VecGetArrayWriteAndMemType(*y, &ya, &my));
-  const int on_device = PetscMemTypeDevice(mx) && PetscMemTypeDevice(my);
-  B200_CHECK(pflare_b200_inv_apply(*handle, 1, PFLARE_B200_INV_AFF, xa, ya, on_device));
-  if (on_device) B200_CHECK(pflare_b200_synchronize(*handle));
-  PetscCallVoid(VecRestoreArrayReadAndMemType(*x, &xa));
-  PetscCallVoid(VecRestoreArrayWriteAndMemType(*y, &ya));
+  cudaStream_t       ps = NULL;
+  B200Aux           *aux = (B200Aux *)*aux_p;
+  const int          kind = b200_get_arrays(*x, *y, &xa, &ya);
+  if (kind == 1) b200_order_in(*handle, aux, &ps);
+  B200_CHECK(pflare_b200_inv_apply(*handle, 1, PFLARE_B200_INV_AFF, xa, ya, kind == 1));
+  if (kind == 1) b200_order_out(*handle, aux, ps);
+  b200_restore_arrays(*x, *y, kind, &xa, &ya);
 }
 
+/* ---- hierarchy container dump (pflare_b200/petsc_io.py documents the object order): one binary viewer, MatView /
+ * ISView / VecView back to back.  Called from the upload hook when -pc_air_b200_dump <file> is given; together with a
+ * PCApply input / output pair written by the same viewer it is the vector-level parity pin of this library. */
+PETSC_INTERN void pflare_b200_dump_ints_c(PetscViewer *viewer, PetscInt n, const PetscInt *vals)
+{
+  IS is;
+  PetscCallVoid(ISCreateGeneral(PETSC_COMM_SELF, n, vals, PETSC_USE_POINTER, &is));
+  PetscCallVoid(ISView(is, *viewer));
+  PetscCallVoid(ISDestroy(&is));
+}
+PETSC_INTERN void pflare_b200_dump_mat_c(PetscViewer *viewer, Mat *A) { PetscCallVoid(MatView(*A, *viewer)); }
+PETSC_INTERN void pflare_b200_dump_vec_c(PetscViewer *viewer, Vec *v) { PetscCallVoid(VecView(*v, *viewer)); }
+
 PETSC_INTERN void pflare_b200_finalize_c(void **handle) { B200_CHECK(pflare_b200_finalize_setup(*handle)); }
-PETSC_INTERN void pflare_b200_destroy_c(void **handle) { if (*handle) B200_CHECK(pflare_b200_destroy(handle)); }
+PETSC_INTERN void pflare_b200_destroy_c(void **handle, void **aux_p)
+{
+  if (*handle) B200_CHECK(pflare_b200_destroy(handle));
+  if (*aux_p) {
+    B200Aux *aux = (B200Aux *)*aux_p;
+    cudaEventDestroy(aux->ev_in);
+    cudaEventDestroy(aux->ev_out);
+    PetscCallVoid(PetscFree(aux));
+    *aux_p = NULL;
+  }
+}
