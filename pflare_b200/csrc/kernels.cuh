@@ -47,6 +47,7 @@ struct SpmvOp {
   const double *val;
   int m, nblk;
   const int *blk;
+  const int *rowmap;           // stream kernel on a row subset (the rows longer than a warp tile): CSR row r is operator row rowmap[r]
   const TileDesc *tiles;       // tile list of the round-1 TMA kernel
   int ntiles;
   // warp-tile storage (kernel 2)
@@ -270,7 +271,7 @@ __device__ __forceinline__ void process_block(const SpmvOp &op, int b, double *p
       if (op.wlast) { --q; xw = prod[q]; }
       double sum = 0.0;
       for (; p < q; ++p) sum += prod[p];
-      row_epilogue(op, r, sum, xw);
+      row_epilogue(op, op.rowmap ? op.rowmap[r] : r, sum, xw);
     }
     __syncthreads();
   } else {
@@ -286,7 +287,7 @@ __device__ __forceinline__ void process_block(const SpmvOp &op, int b, double *p
       double sum = 0.0;
       for (int w = 0; w < NT / 32; ++w) sum += red[w];
       const double xw = op.wlast ? op.val[last] * gather_x(op, op.col[last]) : 0.0;
-      row_epilogue(op, r0, sum, xw);
+      row_epilogue(op, op.rowmap ? op.rowmap[r0] : r0, sum, xw);
     }
     __syncthreads();
   }

@@ -122,7 +122,11 @@ struct DevCSR {
   unsigned char *blob = nullptr;
   WtDesc *wdesc = nullptr;
   int nwt = 0, nwt_int = 0, kp = 8, fmt = 2;
-  bool wt = false;         // this operator runs on the warp-tile kernel (no row longer than a tile)
+  bool wt = false;         // this operator runs on the warp-tile kernels
+  // rows longer than a warp tile (> 256 nonzeros): compact CSR of just those rows for the stream kernel
+  int nlong = 0;
+  int *lrp = nullptr, *lcol = nullptr, *lrow = nullptr, *lblk = nullptr;
+  double *lval = nullptr;
   DevPlan *xp = nullptr;   // ghost exchange (multi-rank)
   bool is_set = false;
   bool valid() const { return is_set; }
@@ -347,29 +351,45 @@ int upload_csr(Ctx *c, const HostCSR &h, DevCSR *d, int space_kind = SP_F, int s
     // short rows: chunk format (no padding inside rows); longer rows: row-aligned lanes (coalesced gathers)
     const double mean_len = h.m > 0 ? (double)h.nnz() / h.m : 0.0;
     const bool chunk = c->wt_format == 1 || (c->wt_format == 0 && mean_len < c->fmt_split);
+    std::vector<int> long_rows;
     if (chunk) {
       WcHost W;
       build_wc(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), &W);
-      if (W.ok) {
-        d->wt = true; d->kp = W.rq; d->fmt = 1;
-        d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
-        if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
-        if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
-        d->ntiles = d->nwt; d->ntiles_int = d->nwt_int;
-        return 0;
-      }
+      d->wt = true; d->kp = W.rq; d->fmt = 1;
+      d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
+      if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
+      if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
+      long_rows.swap(W.long_rows);
     } else {
       WtHost W;
       build_wt(h.m, h.n, h.ia.data(), h.ja.data(), h.a.data(), wfirst, &W);
-      if (W.ok) {
-        d->wt = true; d->kp = W.kp; d->fmt = 2;
-        d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
-        if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
-        if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
-        d->ntiles = d->nwt; d->ntiles_int = d->nwt_int;
-        return 0;
-      }
+      d->wt = true; d->kp = W.kp; d->fmt = 2;
+      d->nwt = (int)W.desc.size(); d->nwt_int = W.n_int;
+      if ((rc = dev_upload(c, &d->blob, W.blob))) return rc;
+      if ((rc = dev_upload(c, &d->wdesc, W.desc))) return rc;
+      long_rows.swap(W.long_rows);
     }
+    d->ntiles = d->nwt; d->ntiles_int = d->nwt_int;
+    d->nlong = (int)long_rows.size();
+    if (d->nlong > 0) {
+      // the few rows longer than a tile: compact CSR (entries in the operator's order, W entry last) + row map + one block per row
+      std::vector<int> lrp(1, 0), lcol, lblk((size_t)d->nlong + 1);
+      std::vector<double> lval;
+      for (int k = 0; k < d->nlong; ++k) {
+        const int r = long_rows[(size_t)k];
+        lcol.insert(lcol.end(), h.ja.begin() + h.ia[r], h.ja.begin() + h.ia[r + 1]);
+        lval.insert(lval.end(), h.a.begin() + h.ia[r], h.a.begin() + h.ia[r + 1]);
+        lrp.push_back((int)lcol.size());
+        lblk[(size_t)k] = k;
+      }
+      lblk[(size_t)d->nlong] = d->nlong;
+      if ((rc = dev_upload_padded(c, &d->lrp, lrp, 8))) return rc;
+      if ((rc = dev_upload_padded(c, &d->lcol, lcol, 8))) return rc;
+      if ((rc = dev_upload_padded(c, &d->lval, lval, 8))) return rc;
+      if ((rc = dev_upload(c, &d->lrow, long_rows))) return rc;
+      if ((rc = dev_upload(c, &d->lblk, lblk))) return rc;
+    }
+    return 0;
   }
   // CSR stream (kernel 0 / 1, or a row longer than a warp tile)
   if ((rc = dev_upload_padded(c, &d->rp, h.ia, 8))) return rc;
@@ -534,6 +554,7 @@ struct Builder {
       else ob.s.tiles = A.tiles + A.ntiles_int;
       Op wt; wt.kind = OPK_XWAIT; wt.level = level; wt.tag = 10;
       out->push_back(oi); out->push_back(wt); out->push_back(ob);
+      push_long_rows(o, A);
       return;
     }
     if (p2p) {
@@ -542,11 +563,26 @@ struct Builder {
       o.s.gw_srcmask = A.xp->srcmask;
     }
     out->push_back(o);
+    push_long_rows(o, A);
     if (p2p) {   // tell the producers that this rank is done with the ghosts of this instance
       Op a;
       a.kind = OPK_ACK; a.xp = A.xp; a.inst = inst; a.level = level; a.tag = 10;
       out->push_back(a);
     }
+  }
+  // The rows longer than a warp tile are not in the operator's tiles: the same op (same epilogue, disjoint rows) runs once
+  // more over a compact CSR of just those rows on the stream kernel.  Multi-rank programs carry the (possibly empty) op
+  // on every rank so that the ranks' op lists keep the same shape.
+  void push_long_rows(const Op &main, const DevCSR &A) {
+    if (!A.wt || (A.nlong == 0 && c->nranks == 1)) return;
+    Op l = main;
+    l.s.blob = nullptr; l.s.wdesc = nullptr; l.s.nwt = 0; l.s.tiles = nullptr;
+    l.s.rp = A.lrp; l.s.col = A.lcol; l.s.val = A.lval; l.s.rowmap = A.lrow;
+    l.s.m = A.nlong; l.s.nblk = A.nlong; l.s.blk = A.lblk; l.s.ntiles = A.nlong;
+    l.s.epi = EPI_GENERIC;
+    l.s.gw_ready = nullptr;   // the main op already waited for (and acknowledges) the ghosts
+    l.bytes = 0; l.nnz = 0;
+    out->push_back(l);
   }
   // out (=|+=) alpha * a .* b ./ dv
   void push_ew(int n, const double *a, const double *b, const double *dv, double alpha, double *dst, int mode,

@@ -30,7 +30,8 @@ constexpr int kWtStageBytes = kWtSlots * 384 + 32;    // shared-memory bytes of 
 struct alignas(16) WtDesc { unsigned off16; int r0; int nrows; int geom; };
 
 struct WtHost {
-  bool ok = false;          // false: some row is longer than a tile -> the operator stays on the CSR stream kernel
+  bool ok = false;
+  std::vector<int> long_rows;   // rows longer than a tile (kWtMaxRow): left out of the tiles, handled by the CSR stream kernel
   int kp = 8;               // slots per lane of a sub-tile (1, 2, 4 or 8); a tile holds <= 8 / kp sub-tiles
   std::vector<unsigned char> blob;
   std::vector<WtDesc> desc;
@@ -38,20 +39,28 @@ struct WtHost {
   int64_t slots = 0;        // stored slots (nonzeros + padding)
 };
 
-// sub-tile boundaries for a given kp: rows [sb[t], sb[t+1]) share one 32-lane sub-tile
-// (false: some row needs more than 32 lanes with this kp)
-inline bool wt_pack(int m, const int *ia, int kp, std::vector<int> *sb) {
+// sub-tiles for a given kp: rows [sb[2t], sb[2t+1]) share one 32-lane sub-tile; rows longer than kWtMaxRow are skipped
+// (they end the running sub-tile; brk[t] = 1 marks a sub-tile that follows such a gap)
+// (false: some row that fits a tile needs more than 32 lanes with this kp)
+inline bool wt_pack(int m, const int *ia, int kp, std::vector<int> *sb, std::vector<unsigned char> *brk = nullptr) {
   sb->clear();
-  sb->push_back(0);
+  if (brk) brk->clear();
+  bool gap = false;
   for (int r = 0; r < m;) {
+    if (ia[r + 1] - ia[r] > kWtMaxRow) { ++r; gap = true; continue; }
+    const int r0 = r;
     int lanes = 0;
     while (r < m) {
-      const int g = (std::max(ia[r + 1] - ia[r], 1) + kp - 1) / kp;
+      const int len = ia[r + 1] - ia[r];
+      if (len > kWtMaxRow) break;
+      const int g = (std::max(len, 1) + kp - 1) / kp;
       if (g > 32) return false;
       if (lanes + g > 32) break;
       lanes += g; ++r;
     }
-    sb->push_back(r);
+    sb->push_back(r0); sb->push_back(r);
+    if (brk) brk->push_back(gap ? 1 : 0);
+    gap = false;
   }
   return true;
 }
@@ -59,36 +68,40 @@ inline bool wt_pack(int m, const int *ia, int kp, std::vector<int> *sb) {
 // wfirst: every row's LAST stored entry (the W entry of the merged A_fc|W operator) is moved to the front
 inline void build_wt(int m, int n_local, const int *ia, const int *ja, const double *a, bool wfirst, WtHost *W) {
   W->ok = true;
+  W->long_rows.clear();
   for (int i = 0; i < m; ++i)
-    if (ia[i + 1] - ia[i] > kWtMaxRow) { W->ok = false; return; }
+    if (ia[i + 1] - ia[i] > kWtMaxRow) W->long_rows.push_back(i);
   // slots per lane: the largest kp whose padded size is within 6 % of the smallest
   std::vector<int> sb;
+  std::vector<unsigned char> brk;
   int64_t best = -1, cost[4];
   const int kps[4] = {8, 4, 2, 1};
   for (int k = 0; k < 4; ++k) {
-    cost[k] = wt_pack(m, ia, kps[k], &sb) ? (int64_t)(sb.size() - 1) * 32 * kps[k] : -1;
+    cost[k] = wt_pack(m, ia, kps[k], &sb) ? (int64_t)(sb.size() / 2) * 32 * kps[k] : -1;
     if (cost[k] >= 0 && (best < 0 || cost[k] < best)) best = cost[k];
   }
   int kp = 8;
   for (int k = 0; k < 4; ++k)
     if (cost[k] >= 0 && (double)cost[k] <= 1.06 * (double)best) { kp = kps[k]; break; }
   W->kp = kp;
-  wt_pack(m, ia, kp, &sb);
-  const size_t nsub = sb.size() - 1;
+  wt_pack(m, ia, kp, &sb, &brk);
+  const size_t nsub = sb.size() / 2;
   const int per = kWtSlots / kp;                         // sub-tiles per tile
-  const size_t nt = (nsub + per - 1) / per;
   W->slots = (int64_t)nsub * 32 * kp;
+  // tiles = runs of <= per consecutive sub-tiles with contiguous rows (a skipped long row ends the tile)
+  std::vector<size_t> tfirst;                            // first sub-tile of every tile (+ sentinel)
+  for (size_t q = 0; q < nsub; ++q)
+    if (tfirst.empty() || brk[q] || q - tfirst.back() == (size_t)per) tfirst.push_back(q);
+  const size_t nt = tfirst.size();
+  tfirst.push_back(nsub);
   std::vector<size_t> off(nt + 1, 0);
-  for (size_t t = 0; t < nt; ++t) {
-    const size_t ns = std::min<size_t>(per, nsub - t * per);
-    off[t + 1] = off[t] + ns * kp * 384 + 32;
-  }
+  for (size_t t = 0; t < nt; ++t) off[t + 1] = off[t] + (tfirst[t + 1] - tfirst[t]) * kp * 384 + 32;
   W->blob.assign(off[nt] + 16, 0);
   std::vector<WtDesc> desc(nt);
   std::vector<unsigned char> ghost(nt, 0);
 #pragma omp parallel for schedule(dynamic, 256)
   for (size_t t = 0; t < nt; ++t) {
-    const int ns = (int)std::min<size_t>(per, nsub - t * per);
+    const int ns = (int)(tfirst[t + 1] - tfirst[t]);
     const int nslots = ns * kp;
     unsigned char *b = W->blob.data() + off[t];
     double *val = reinterpret_cast<double *>(b);
@@ -97,9 +110,9 @@ inline void build_wt(int m, int n_local, const int *ia, const int *ja, const dou
     int gmax = 1;
     bool gh = false;
     for (int s = 0; s < ns; ++s) {
-      const size_t st = t * per + s;
+      const size_t st = tfirst[t] + s;
       int lane = 0;
-      for (int r = sb[st]; r < sb[st + 1]; ++r) {
+      for (int r = sb[2 * st]; r < sb[2 * st + 1]; ++r) {
         const int s0 = ia[r], len = ia[r + 1] - s0;
         const int g = (std::max(len, 1) + kp - 1) / kp;
         gmax = std::max(gmax, g);
@@ -116,7 +129,7 @@ inline void build_wt(int m, int n_local, const int *ia, const int *ja, const dou
       }
     }
     ghost[t] = gh ? 1 : 0;
-    desc[t] = WtDesc{(unsigned)(off[t] / 16), sb[t * per], sb[t * per + ns] - sb[t * per], ns | (gmax << 8)};
+    desc[t] = WtDesc{(unsigned)(off[t] / 16), sb[2 * tfirst[t]], sb[2 * (tfirst[t] + ns) - 1] - sb[2 * tfirst[t]], ns | (gmax << 8)};
   }
   // interior tiles first: they can be multiplied while the ghost exchange is still in flight
   W->desc.clear();
@@ -143,7 +156,8 @@ constexpr int kWcTileNnz = 32 * kWcKpl;            // 256
 constexpr int kWcStageBytes = kWcKpl * 384 + 64;   // shared-memory bytes of one ring slot
 
 struct WcHost {
-  bool ok = false;          // false: some row is longer than a tile -> the operator stays on the CSR stream kernel
+  bool ok = false;
+  std::vector<int> long_rows;   // rows longer than a tile: left out of the tiles, handled by the CSR stream kernel
   int rq = 1;               // rows per lane of a tile
   std::vector<unsigned char> blob;
   std::vector<WtDesc> desc;
@@ -160,23 +174,23 @@ inline int wc_rows_per_lane(double mean_len) {
 
 inline void build_wc(int m, int n_local, const int *ia, const int *ja, const double *a, WcHost *W) {
   W->ok = true;
-  for (int i = 0; i < m; ++i)
-    if (ia[i + 1] - ia[i] > kWcTileNnz) { W->ok = false; return; }
+  W->long_rows.clear();
   W->rq = wc_rows_per_lane(m > 0 ? (double)ia[m] / m : 1.0);
   const int maxrows = 32 * W->rq;
-  // pass 1: greedy tile boundaries (an empty row counts as one explicit zero entry)
+  // pass 1: greedy tiles [tb[2t], tb[2t+1]) (an empty row counts as one explicit zero entry; a row longer than a tile is skipped)
   std::vector<int> tb;
-  tb.push_back(0);
   for (int r = 0; r < m;) {
+    if (ia[r + 1] - ia[r] > kWcTileNnz) { W->long_rows.push_back(r); ++r; continue; }
     int n = 0, r0 = r;
     while (r < m && r - r0 < maxrows) {
+      if (ia[r + 1] - ia[r] > kWcTileNnz) break;
       const int len = std::max(ia[r + 1] - ia[r], 1);
       if (n + len > kWcTileNnz) break;
       n += len; ++r;
     }
-    tb.push_back(r);
+    tb.push_back(r0); tb.push_back(r);
   }
-  const size_t nt = tb.size() - 1;
+  const size_t nt = tb.size() / 2;
   std::vector<int> tn(nt);                 // entries per tile
   std::vector<size_t> off(nt + 1, 0);      // blob offsets (bytes)
   std::vector<unsigned char> ghost(nt, 0);
@@ -184,7 +198,7 @@ inline void build_wc(int m, int n_local, const int *ia, const int *ja, const dou
   for (size_t t = 0; t < nt; ++t) {
     int n = 0;
     bool g = false;
-    for (int r = tb[t]; r < tb[t + 1]; ++r) {
+    for (int r = tb[2 * t]; r < tb[2 * t + 1]; ++r) {
       n += std::max(ia[r + 1] - ia[r], 1);
       for (int p = ia[r]; p < ia[r + 1] && !g; ++p) g = ja[p] >= n_local;
     }
@@ -201,7 +215,7 @@ inline void build_wc(int m, int n_local, const int *ia, const int *ja, const dou
     int *col = reinterpret_cast<int *>(b + (size_t)kpl * 256);
     unsigned short *ends = reinterpret_cast<unsigned short *>(b + (size_t)kpl * 384);
     int p = 0;   // position inside the tile: lane = p / kpl, slot = p % kpl
-    for (int r = tb[t]; r < tb[t + 1]; ++r) {
+    for (int r = tb[2 * t]; r < tb[2 * t + 1]; ++r) {
       const int s0 = ia[r], s1 = ia[r + 1];
       if (s1 == s0) {          // empty row: explicit 0.0 * x[0]
         ends[p / kpl] |= (unsigned short)(1u << (p % kpl));
@@ -215,7 +229,7 @@ inline void build_wc(int m, int n_local, const int *ia, const int *ja, const dou
         if (q + 1 == s1) ends[lane] |= (unsigned short)(1u << j);
       }
     }
-    desc[t] = WtDesc{(unsigned)(off[t] / 16), tb[t], tb[t + 1] - tb[t], kpl};
+    desc[t] = WtDesc{(unsigned)(off[t] / 16), tb[2 * t], tb[2 * t + 1] - tb[2 * t], kpl};
   }
   // interior tiles first: they can be multiplied while the ghost exchange is still in flight
   W->desc.clear();

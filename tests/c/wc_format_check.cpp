@@ -70,7 +70,7 @@ static void tile_rows(const WcHost &W, const WtDesc &d, const std::vector<double
     }
 }
 
-static int run_case(int m, int n, double mean_len, double p_empty, bool wlast, int n_ghost, unsigned seed) {
+static int run_case(int m, int n, double mean_len, double p_empty, bool wlast, int n_ghost, unsigned seed, int len_cap = kWcTileNnz) {
   std::mt19937 rng(seed);
   std::uniform_real_distribution<double> U(0.0, 1.0);
   std::vector<int> ia(1, 0), ja;
@@ -79,7 +79,7 @@ static int run_case(int m, int n, double mean_len, double p_empty, bool wlast, i
     int len = 0;
     if (U(rng) >= p_empty) {
       len = 1 + (int)(-std::log(1.0 - U(rng) * 0.999) * (mean_len - 1.0));
-      if (len > kWcTileNnz) len = kWcTileNnz;
+      if (len > len_cap) len = len_cap;
     }
     if (wlast && len == 0) len = 1;   // the merged A_fc|W operator always has the W entry
     for (int k = 0; k < len; ++k) { ja.push_back((int)(U(rng) * (n + n_ghost)) % (n + n_ghost)); a.push_back(U(rng) - 0.5); }
@@ -106,6 +106,15 @@ static int run_case(int m, int n, double mean_len, double p_empty, bool wlast, i
     tile_rows(W, d, x, wlast, rs, xw);
   }
   if (bytes + 16 != W.blob.size()) { printf("FAIL: blob size %zu vs tiles %zu\n", W.blob.size(), bytes); return 1; }
+  for (int i : W.long_rows) {   // rows left to the CSR stream kernel
+    if (ia[i + 1] - ia[i] <= kWcTileNnz) { printf("FAIL: row %d listed as long\n", i); return 1; }
+    covered[i]++;
+    double sl = 0.0;
+    const int q1 = wlast ? ia[i + 1] - 1 : ia[i + 1];
+    for (int q = ia[i]; q < q1; ++q) sl += a[q] * x[ja[q]];
+    rs[i] = sl;
+    if (wlast) xw[i] = a[q1] * x[ja[q1]];
+  }
   double maxerr = 0.0;
   for (int i = 0; i < m; ++i) {
     if (covered[i] != 1) { printf("FAIL: row %d covered %d times\n", i, covered[i]); return 1; }
@@ -132,13 +141,18 @@ int main() {
   bad += run_case(1, 1, 1.0, 0.0, false, 0, 5); ++n;          // one row
   bad += run_case(40, 10, 1.0, 1.0, false, 0, 6); ++n;        // every row empty
   bad += run_case(257, 64, 256.0, 0.0, false, 0, 7); ++n;     // rows of (up to) a whole tile
-  // a row longer than a tile must be refused (the operator then stays on the CSR stream kernel)
+  bad += run_case(900, 700, 150.0, 0.02, false, 40, 8, 700); ++n;   // some rows longer than a tile: skipped by the tiles, listed
+  bad += run_case(900, 700, 120.0, 0.0, true, 0, 9, 700); ++n;
+  // a row longer than a tile is left out of the tiles and listed (it then runs on the CSR stream kernel)
   {
-    std::vector<int> ia = {0, kWcTileNnz + 1}, ja((size_t)kWcTileNnz + 1, 0);
-    std::vector<double> a((size_t)kWcTileNnz + 1, 1.0);
+    const int L = kWcTileNnz + 5;
+    std::vector<int> ia = {0, 2, 2 + L, 2 + L + 3}, ja((size_t)L + 5, 0);
+    std::vector<double> a((size_t)L + 5, 1.0);
     WcHost W;
-    build_wc(1, 1, ia.data(), ja.data(), a.data(), &W);
-    if (W.ok) { printf("FAIL: long row accepted\n"); ++bad; }
+    build_wc(3, 1, ia.data(), ja.data(), a.data(), &W);
+    int rows = 0;
+    for (const WtDesc &d : W.desc) rows += d.nrows;
+    if (!W.ok || W.long_rows.size() != 1 || W.long_rows[0] != 1 || rows != 2 || W.desc.size() != 2) { printf("FAIL: long row handling\n"); ++bad; }
     ++n;
   }
   printf("%s: %d cases, %d failed\n", bad ? "WC_FORMAT_FAIL" : "WC_FORMAT_OK", n, bad);

@@ -238,21 +238,42 @@ def test_edge_cases(built_libs):
     p2.destroy()
 
 
-def test_rows_longer_than_a_tile(built_libs):
-    """A dense-ish coarse operator: rows longer than the kernel's nnz tile take the whole-CTA path."""
+@pytest.mark.parametrize("opts", [dict(), dict(wt_format=1), dict(wt_format=2), dict(wt_format=2, engine=0), dict(wt_format=2, engine=2),
+                                  dict(kernel=0), dict(kernel=1)], ids=str)
+def test_rows_longer_than_a_tile(built_libs, opts):
+    """A dense-ish operator: the rows longer than a warp tile (> 256 nonzeros) are left out of the tiles and run on the
+    CSR stream kernel (whole-CTA reduction), the others stay on the warp-tile kernels."""
     import scipy.sparse as sp
     rng = np.random.default_rng(3)
     n = 3000
     D = sp.random(n, n, density=0.002, random_state=5, format="lil")
     D[7, :] = rng.random(n)            # one 3000-nnz row
     D[11, :2500] = rng.random(2500)
+    D[12, :300] = rng.random(300)      # just above a tile
+    D[2999, 100:700] = rng.random(600)
     A = (D.tocsr() + sp.identity(n) * 50.0).tocsr()
     H = hiergen.build_pflareinv(A, poly.ARNOLDI, 4, 1, True)
     x = cases.rhs(n)
     yo = _oracle(H).inv_apply(1, oracle.INV_AFF, x)
     pc = pflare_b200.PC().setType("pflareinv").setHierarchy(H)
+    for k, v in opts.items():
+        pc.setOption(k, v)
     assert cases.rel_l2(pc.apply(x), yo) <= TOL
     pc.destroy()
+
+
+def test_vcycle_with_long_rows_on_the_coarse_levels(built_libs):
+    """3D diffusion-dominated hierarchy without the dense tail: the coarse operators have rows of several hundred nonzeros."""
+    A = hiergen.adv_diff_fd(14, 14, 14, alpha=1.0)
+    H = hiergen.build_hierarchy(A, hiergen.AirOptions(a_drop=0.0, r_drop=0.0))
+    longest = max(int(np.diff(m.indptr).max()) for lv in H.levels for m in (lv.A_ff, lv.A_fc, lv.R))
+    assert longest > 256, longest
+    b = cases.rhs(A.shape[0])
+    xo = _oracle(H).apply(b)
+    for opts in (dict(dense_rows=0), dict(dense_rows=0, wt_format=1), dict(dense_rows=0, wt_format=2, engine=0)):
+        d = _device(H, **opts)
+        assert cases.rel_l2(d.apply(b), xo) <= TOL, opts
+        d.close()
 
 
 def test_medium_size_parity_and_linearity(built_libs):
