@@ -213,8 +213,7 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
  *                  kernel with CTA tiles (A/B baseline), 2 = warp-tile storage (default);
  *   "wt_format" / "fmt_split" (before finalize_setup) warp-tile storage per operator: 0 = by mean row length (< fmt_split, default 8:
  *                  chunk format, else row-aligned lanes), 1 / 2 = force one of them;
- *   "engine" kernel of the row-aligned storage: 0 = TMA ring, 1 = direct (default), 2 = thin warps; "sv_minb" resident CTAs per SM the
- *                  direct engine is compiled for (3, 4 default, 5); "wt_stages" ring depth of the TMA engines (2 default, 3);
+ *   "engine" kernel of the row-aligned storage: 1 = direct (default), 0 = TMA ring (A/B);
  *   "ctas_per_sm" / "max_ctas" caps on the persistent grids (tests: many tiles per warp);
  *   "dense_rows" levels with <= this many rows are collapsed into one dense operator built from the same kernels at setup (0 = off);
  *   "fuse_perm" (before finalize_setup) 0 (default) / 1 / 2: entry / exit permutation fused into the level-1 ops (measured slower);

@@ -668,11 +668,13 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wc_kernel(const SpmvOp op) {
 // (32 lanes x 4 / 8 bytes per slot, streaming cache policy), so a warp simply loads its slots, gathers
 // x, multiplies and reduces; the head lane of every row runs the row epilogue (consecutive rows ->
 // consecutive head lanes -> the vector accesses still fill whole sectors).  With no shared-memory
-// ring and ~80 registers, 24 warps per SM are resident (the TMA-ring engine: 16) and the whole L1
-// serves the gathers: latency is hidden by occupancy instead of by a software pipeline.
+// ring and 64 registers, 32 warps per SM are resident (the TMA-ring engine: 16) and the whole L1
+// serves the gathers: latency is hidden by occupancy instead of by a software pipeline.  Measured on
+// the 4096^2 cycle: 3 / 4 / 5 CTAs per SM (80 / 64 / 48 registers) -> 2.62 / 2.56 / 3.01 ms; a 40-register
+// "thin warp" variant with 48 warps per SM (tools/microbench/r02_thin_engine.cuh) -> 2.76 ms.
 __device__ __forceinline__ int ld_stream_nc(const int *p) { return __ldcs(p); }
-template <int EPI, int KP, bool GHOST, int MINB>
-__global__ void __launch_bounds__(256, MINB) spmv_sv_kernel(const SpmvOp op) {
+template <int EPI, int KP, bool GHOST>
+__global__ void __launch_bounds__(256, 4) spmv_sv_kernel(const SpmvOp op) {
   typedef EpiT<EPI> E;
   typedef typename E::Pre Pre;
   constexpr bool XW = E::kXw;
@@ -768,86 +770,6 @@ __global__ void __launch_bounds__(256, MINB) spmv_sv_kernel(const SpmvOp op) {
           E::finish(op, row[s], acc, xw, pc[s]);
         }
       }
-    }
-  }
-  if (!waited) pdl_wait();
-}
-
-// ------------------------------------------------------------------------------------------
-// Thin-warp engine on the same storage: the direct engine cut down to ~40 registers so that 48 warps per
-// SM are resident.  A warp walks its tile sub-tile by sub-tile, at most 4 slots per lane in flight
-// (coalesced streaming loads of columns and values, gathers, fused multiply-adds), a segmented shuffle
-// reduction per sub-tile, and the head lane of every row loads its epilogue operands and finishes the row.
-// Nothing is software-pipelined: every latency (matrix stream, gathers, epilogue operands) is hidden by
-// the other 47 warps of the SM -- the measured behaviour of all three engines is "throughput
-// proportional to resident warps", so this one maximises them.
-template <int EPI, int KP, bool GHOST>
-__global__ void __launch_bounds__(256, 6) spmv_thin_kernel(const SpmvOp op) {
-  typedef EpiT<EPI> E;
-  constexpr bool XW = E::kXw;
-  constexpr int CH = KP < 4 ? KP : 4;   // slots per lane in flight
-  constexpr int NCH = KP / CH;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const WtDesc *__restrict__ wdesc = op.wdesc;
-  const double *__restrict__ xv = op.x;
-  const double *__restrict__ xg = op.xg;
-  const int nloc = op.nloc;
-  const bool wf = (EPI == EPI_AFCW || EPI == EPI_AFCW_LOCAL) || (EPI == EPI_GENERIC && op.wlast);
-  pdl_launch_dependents();
-  bool waited = false;
-  for (int t = gw; t < op.nwt; t += nwarps) {
-    const WtDesc d = wdesc[t];
-    const int ns = d.geom & 0xff, gmax = d.geom >> 8;
-    const int nslots = ns * KP;
-    const unsigned char *b = op.blob + (size_t)d.off16 * 16;
-    const double *val_g = reinterpret_cast<const double *>(b) + lane;
-    const int *col_g = reinterpret_cast<const int *>(b + nslots * 256) + lane;
-    const unsigned *heads = reinterpret_cast<const unsigned *>(b + nslots * 384);
-    int rowbase = d.r0;
-    for (int s = 0; s < ns; ++s) {
-      const unsigned H = __ldg(heads + s);
-      const bool head = (H >> lane) & 1u;
-      double acc = 0.0, xw = 0.0;
-#pragma unroll
-      for (int h = 0; h < NCH; ++h) {
-        int c[CH];
-        double v[CH];
-#pragma unroll
-        for (int j = 0; j < CH; ++j) c[j] = __ldcs(col_g + (s * KP + h * CH + j) * 32);
-#pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = __ldcs(val_g + (s * KP + h * CH + j) * 32);
-        if (!waited) {   // from here on the vectors written by the previous kernels are read
-          pdl_wait();
-          waited = true;
-          if (GHOST) { if (lane == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask); __syncwarp(); }
-        }
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          double x;
-          if (GHOST) x = (c[j] >= nloc) ? __ldcg(xg + (c[j] - nloc)) : xv[c[j]];
-          else x = xv[c[j]];
-          if (XW && h == 0 && j == 0 && wf && head) xw = v[j] * x;   // merged A_fc|W: the row's first entry is the W entry
-          else acc += v[j] * x;
-        }
-      }
-      if (gmax > 1) {
-        const unsigned above = lane < 31 ? (H >> (lane + 1)) : 0u;
-        const int dist = above ? __ffs((int)above) - 1 : 31 - lane;   // lanes of my row after me
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          if (o < gmax) {
-            const double tt = __shfl_down_sync(0xffffffffu, acc, o);
-            if (o <= dist) acc += tt;
-          }
-        }
-      }
-      if (head) {
-        const int r = rowbase + __popc(H & ((1u << lane) - 1u));
-        E::finish(op, r, acc, xw, E::prefetch(op, r));
-      }
-      rowbase += __popc(H);
     }
   }
   if (!waited) pdl_wait();

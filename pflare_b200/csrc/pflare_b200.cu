@@ -226,8 +226,7 @@ struct Ctx {
   int kernel = 2;        // 0: smem-staged stream kernel, 1: round-1 TMA kernel (CTA tiles), 2: warp-tile kernel
   int wt_format = 0;     // kernel 2 operator storage: 0 = by mean row length (fmt_split), 1 = chunk format, 2 = row-aligned lanes
   double fmt_split = 8.0;   // measured on the 4096^2 cycle: 3 -> 2.82 ms, 4.5 -> 2.65 ms, 8 -> 2.62 ms
-  int engine = 1;        // kernel 2 (row-aligned format): 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
-  int sv_minb = 4;       // direct engine: resident CTAs per SM it is compiled for (3: 80 registers, 4: 64, 5: 48); measured 2.62 / 2.56 ms at 3 / 4
+  int engine = 1;        // kernel 2, row-aligned storage: 1 = direct engine (spmv_sv_kernel), 0 = TMA-ring engine (spmv_wt_kernel, A/B) // 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
   int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
@@ -968,21 +967,9 @@ int launch_wt_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   return 0;
 }
 // direct engine (no shared memory): one instantiation per (epilogue class, slots per lane, ghost columns)
-template <int EPI, int KP, bool GH, int MINB>
-int launch_sv_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_sv_kernel<EPI, KP, GH, MINB>;
-  static int per_sm = 0;
-  int rc = kernel_per_sm(kern, 256, 0, &per_sm);
-  if (rc || dry) return rc;
-  const int want = c->ctas_per_sm > 0 ? std::min(c->ctas_per_sm, per_sm) : per_sm;
-  int grid = std::min((s.nwt + 7) / 8, c->num_sms * want);   // persistent, 8 warps per CTA
-  if (c->max_ctas > 0) grid = std::min(grid, c->max_ctas);
-  CUDA_TRY(launch_k(c->pdl != 0, kern, grid, 256, 0, st, s));
-  return 0;
-}
 template <int EPI, int KP, bool GH>
-int launch_thin_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_thin_kernel<EPI, KP, GH>;
+int launch_sv_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
+  auto kern = spmv_sv_kernel<EPI, KP, GH>;
   static int per_sm = 0;
   int rc = kernel_per_sm(kern, 256, 0, &per_sm);
   if (rc || dry) return rc;
@@ -995,11 +982,7 @@ int launch_thin_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
 template <int EPI, int KP>
 int launch_wt_kp(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   const bool gh = s.xg != nullptr;
-  if (c->engine == 2) return gh ? launch_thin_inst<EPI, KP, true>(c, s, st, dry) : launch_thin_inst<EPI, KP, false>(c, s, st, dry);
-  if (c->engine == 1 && c->sv_minb == 5) return gh ? launch_sv_inst<EPI, KP, true, 5>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 5>(c, s, st, dry);
-  if (c->engine == 1 && c->sv_minb == 4) return gh ? launch_sv_inst<EPI, KP, true, 4>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 4>(c, s, st, dry);
-  if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true, 3>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 3>(c, s, st, dry);
-  if (c->wt_stages == 3) return gh ? launch_wt_inst<EPI, KP, true, 3>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 3>(c, s, st, dry);
+  if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true>(c, s, st, dry) : launch_sv_inst<EPI, KP, false>(c, s, st, dry);
   return gh ? launch_wt_inst<EPI, KP, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 2>(c, s, st, dry);
 }
 // chunk-format engine: one instantiation per (epilogue class, rows per lane, ghost columns); TMA ring of 2 tiles
@@ -1549,7 +1532,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
   ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->full_smooth = c->full_smooth; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
-  ch->kernel = c->kernel; ch->wt_format = c->wt_format; ch->fmt_split = c->fmt_split; ch->engine = c->engine; ch->sv_minb = c->sv_minb; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+  ch->kernel = c->kernel; ch->wt_format = c->wt_format; ch->fmt_split = c->fmt_split; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
   for (int l = LA; l <= NL; ++l) {
@@ -2870,15 +2853,11 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
     c->fmt_split = value;
   }
   else if (k == "engine") {
-    if (value != 0 && value != 1 && value != 2) return fail(2, "engine must be 0 (TMA ring), 1 (direct) or 2 (thin warps)");
+    if (value != 0 && value != 1) return fail(2, "engine must be 0 (TMA ring) or 1 (direct)");
     c->engine = (int)value;
   }
-  else if (k == "sv_minb") {
-    if (value != 3 && value != 4 && value != 5) return fail(2, "sv_minb must be 3, 4 or 5");
-    c->sv_minb = (int)value;
-  }
   else if (k == "wt_stages") {
-    if (value != 2 && value != 3) return fail(2, "wt_stages must be 2 or 3");
+    if (value != 2) return fail(2, "wt_stages: only the 2-deep ring is compiled in (3 and 4 deep measured slower: 2.79 / 2.91 / 3.96 ms)");
     c->wt_stages = (int)value;
   }
   else if (k == "dense_rows") {
@@ -2906,7 +2885,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
     Ctx *ch = c->child.get();
-    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->sv_minb = c->sv_minb; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
     ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   }
   return 0;

@@ -78,7 +78,10 @@ class PC:
             feed_fn(self._dev)
         else:
             feed(H, self._dev)
-        self._n = H.local_rows() if hasattr(H, "local_rows") else H.A.shape[0]
+        if hasattr(H, "local_rows"):
+            self._n = H.local_rows()
+        else:      # rows of level 1 (a container read from disk carries no separate copy of the system matrix)
+            self._n = H.levels[0].n if H.levels else H.coarse_matrix.shape[0]
         self._setup = True
         return self
 

@@ -60,7 +60,7 @@ def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
 
 
 @pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=1), dict(dense_rows=0), dict(pdl=0), dict(p2p=1), dict(p2p=1, graph=0), dict(overlap=0), dict(overlap=0, graph=0),
-                                  dict(epi_classes=0), dict(wt_stages=3, p2p=1), dict(max_ctas=1), dict(kernel=1, p2p=1)], ids=str)
+                                  dict(epi_classes=0), dict(engine=0, p2p=1), dict(max_ctas=1), dict(kernel=1, p2p=1)], ids=str)
 def test_partitioned_execution_modes(built_libs, opts):
     A, H = cases.build("fd2d_64")
     b = cases.rhs(A.shape[0], seed=3)

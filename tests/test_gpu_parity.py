@@ -57,13 +57,13 @@ def test_vcycle_parity(built_libs, name, mode):
                                   dict(kernel=1, ctas_per_sm=1),
                                   # kernel 2 engines: 1 = direct (no shared memory, default), 0 = TMA ring; entry / exit permutation fused into level 1
                                   dict(engine=0, dense_rows=0), dict(engine=0), dict(engine=0, max_ctas=1, dense_rows=0), dict(engine=1, max_ctas=1, dense_rows=0),
-                                  dict(engine=1, dense_rows=0), dict(engine=1), dict(wt_format=1, dense_rows=0), dict(wt_format=2, dense_rows=0), dict(wt_format=1, max_ctas=1, dense_rows=0), dict(wt_format=2, engine=2), dict(engine=2, max_ctas=1, dense_rows=0), dict(engine=2, epi_classes=0, dense_rows=0), dict(engine=1, fuse_perm=2),
+                                  dict(engine=1, dense_rows=0), dict(engine=1), dict(wt_format=1, dense_rows=0), dict(wt_format=2, dense_rows=0), dict(wt_format=1, max_ctas=1, dense_rows=0), dict(engine=1, fuse_perm=2),
                                   dict(fuse_perm=2), dict(fuse_perm=2, graph=0, pdl=0), dict(fuse_perm=2, epi_classes=0, dense_rows=0), dict(fuse_perm=2, kernel=0), dict(fuse_perm=2, kernel=1, dense_rows=0),
                                   dict(fuse_perm=0),
                                   # warp-tile kernel: ring depth, generic (run-time branched) epilogue instead of the compiled classes,
                                   # ONE persistent CTA per SM / in total (many tiles per warp: the mbarrier ring wraps many times)
-                                  dict(wt_stages=3, dense_rows=0), dict(epi_classes=0, dense_rows=0), dict(epi_classes=0, fuse=0, dense_rows=0),
-                                  dict(ctas_per_sm=1, dense_rows=0), dict(max_ctas=1, dense_rows=0), dict(max_ctas=1, wt_stages=3, dense_rows=0, graph=0, pdl=0),
+                                  dict(epi_classes=0, dense_rows=0), dict(epi_classes=0, fuse=0, dense_rows=0),
+                                  dict(ctas_per_sm=1, dense_rows=0), dict(max_ctas=1, dense_rows=0), dict(max_ctas=1, dense_rows=0, graph=0, pdl=0),
                                   dict(kernel=1, max_ctas=2, dense_rows=0),
                                   # coarse levels collapsed into one dense operator (built from the same kernels at setup)
                                   dict(dense_rows=600), dict(dense_rows=16384), dict(dense_rows=300, graph=0)],
@@ -238,7 +238,7 @@ def test_edge_cases(built_libs):
     p2.destroy()
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(wt_format=1), dict(wt_format=2), dict(wt_format=2, engine=0), dict(wt_format=2, engine=2),
+@pytest.mark.parametrize("opts", [dict(), dict(wt_format=1), dict(wt_format=2), dict(wt_format=2, engine=0),
                                   dict(kernel=0), dict(kernel=1)], ids=str)
 def test_rows_longer_than_a_tile(built_libs, opts):
     """A dense-ish operator: the rows longer than a warp tile (> 256 nonzeros) are left out of the tiles and run on the

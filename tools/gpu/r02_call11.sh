@@ -1,7 +1,7 @@
 #!/bin/bash
 # long rows outside the tiles: parity (+ dist) and the 3D workload at 160^3
 cd "$(dirname "$0")/../.." ; mkdir -p gpurun_out
-timeout 2400 python -X faulthandler -m pytest tests -x -q -m gpu --timeout 180 > gpurun_out/r11_pytest_gpu.log 2>&1; rc=$?; echo "pytest gpu rc=$rc"; tail -6 gpurun_out/r11_pytest_gpu.log
+timeout 2400 python -X faulthandler -m pytest tests -q -m gpu --timeout 180 > gpurun_out/r11_pytest_gpu.log 2>&1; rc=$?; echo "pytest gpu rc=$rc"; tail -6 gpurun_out/r11_pytest_gpu.log
 [ $rc -ne 0 ] && exit 1
 timeout 900 python bench.py --workload adv_diff_fd_3d_lair --size 160 --steps 20 --warmup 3 --no-cpu-baseline --dump-ops gpurun_out/r11_ops_3d160.csv > gpurun_out/r11_b3d160.json 2> gpurun_out/r11_b3d160.log; echo "3d rc=$?"
 grep "\[bench\]" gpurun_out/r11_b3d160.log | tail -4
