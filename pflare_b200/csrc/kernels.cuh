@@ -673,8 +673,8 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wc_kernel(const SpmvOp op) {
 // the 4096^2 cycle: 3 / 4 / 5 CTAs per SM (80 / 64 / 48 registers) -> 2.62 / 2.56 / 3.01 ms; a 40-register
 // "thin warp" variant with 48 warps per SM (tools/microbench/r02_thin_engine.cuh) -> 2.76 ms.
 __device__ __forceinline__ int ld_stream_nc(const int *p) { return __ldcs(p); }
-template <int EPI, int KP, bool GHOST>
-__global__ void __launch_bounds__(256, 4) spmv_sv_kernel(const SpmvOp op) {
+template <int EPI, int KP, bool GHOST, int PF>   // PF 1: the next tile's column indices are loaded one tile ahead (3 CTAs per SM instead of 4)
+__global__ void __launch_bounds__(256, PF ? 3 : 4) spmv_sv_kernel(const SpmvOp op) {
   typedef EpiT<EPI> E;
   typedef typename E::Pre Pre;
   constexpr bool XW = E::kXw;
@@ -691,12 +691,25 @@ __global__ void __launch_bounds__(256, 4) spmv_sv_kernel(const SpmvOp op) {
   const bool wf = (EPI == EPI_AFCW || EPI == EPI_AFCW_LOCAL) || (EPI == EPI_GENERIC && op.wlast);
   pdl_launch_dependents();
   int t = gw;
-  WtDesc dn = {0u, 0, 0, 0};
+  WtDesc dn = {0u, 0, 0, 0}, dn2 = {0u, 0, 0, 0};
   if (t < op.nwt) dn = wdesc[t];
+  if (PF && t + nwarps < op.nwt) dn2 = wdesc[t + nwarps];
+  int cn[NSLOT];
+  if (PF && t < op.nwt) {
+    const int nsl = (dn.geom & 0xff) * KP;
+    const int *cg = reinterpret_cast<const int *>(op.blob + (size_t)dn.off16 * 16 + nsl * 256);
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) cn[k] = (k < nsl) ? __ldcs(cg + k * 32 + lane) : 0;
+  }
   bool waited = false;
   for (; t < op.nwt; t += nwarps) {
     const WtDesc d = dn;
-    if (t + nwarps < op.nwt) dn = wdesc[t + nwarps];
+    if (PF) {
+      dn = dn2;
+      if (t + 2 * nwarps < op.nwt) dn2 = wdesc[t + 2 * nwarps];
+    } else if (t + nwarps < op.nwt) {
+      dn = wdesc[t + nwarps];
+    }
     const int ns = d.geom & 0xff, gmax = d.geom >> 8;
     const int nslots = ns * KP;
     const unsigned char *b = op.blob + (size_t)d.off16 * 16;
@@ -706,8 +719,19 @@ __global__ void __launch_bounds__(256, 4) spmv_sv_kernel(const SpmvOp op) {
     // matrix stream: coalesced, read once
     int c[NSLOT];
     double p[NSLOT];
+    if (PF) {
 #pragma unroll
-    for (int k = 0; k < NSLOT; ++k) c[k] = (k < nslots) ? __ldcs(col_g + k * 32 + lane) : 0;
+      for (int k = 0; k < NSLOT; ++k) c[k] = cn[k];
+      if (t + nwarps < op.nwt) {   // the next tile's columns: in flight while this tile is gathered, multiplied and reduced
+        const int nsl = (dn.geom & 0xff) * KP;
+        const int *cg = reinterpret_cast<const int *>(op.blob + (size_t)dn.off16 * 16 + nsl * 256);
+#pragma unroll
+        for (int k = 0; k < NSLOT; ++k) cn[k] = (k < nsl) ? __ldcs(cg + k * 32 + lane) : 0;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NSLOT; ++k) c[k] = (k < nslots) ? __ldcs(col_g + k * 32 + lane) : 0;
+    }
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) p[k] = (k < nslots) ? __ldcs(val_g + k * 32 + lane) : 0.0;
     unsigned hd[NS];

@@ -227,6 +227,7 @@ struct Ctx {
   int wt_format = 0;     // kernel 2 operator storage: 0 = by mean row length (fmt_split), 1 = chunk format, 2 = row-aligned lanes
   double fmt_split = 8.0;   // measured on the 4096^2 cycle: 3 -> 2.82 ms, 4.5 -> 2.65 ms, 8 -> 2.62 ms
   int engine = 1;        // kernel 2, row-aligned storage: 1 = direct engine (spmv_sv_kernel), 0 = TMA-ring engine (spmv_wt_kernel, A/B) // 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
+  int sv_pf = 0;         // direct engine: 1 = column indices prefetched one tile ahead (3 CTAs per SM)
   int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
@@ -967,9 +968,9 @@ int launch_wt_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   return 0;
 }
 // direct engine (no shared memory): one instantiation per (epilogue class, slots per lane, ghost columns)
-template <int EPI, int KP, bool GH>
+template <int EPI, int KP, bool GH, int PF>
 int launch_sv_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
-  auto kern = spmv_sv_kernel<EPI, KP, GH>;
+  auto kern = spmv_sv_kernel<EPI, KP, GH, PF>;
   static int per_sm = 0;
   int rc = kernel_per_sm(kern, 256, 0, &per_sm);
   if (rc || dry) return rc;
@@ -982,7 +983,8 @@ int launch_sv_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
 template <int EPI, int KP>
 int launch_wt_kp(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   const bool gh = s.xg != nullptr;
-  if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true>(c, s, st, dry) : launch_sv_inst<EPI, KP, false>(c, s, st, dry);
+  if (c->engine == 1 && c->sv_pf) return gh ? launch_sv_inst<EPI, KP, true, 1>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 1>(c, s, st, dry);
+  if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true, 0>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 0>(c, s, st, dry);
   return gh ? launch_wt_inst<EPI, KP, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 2>(c, s, st, dry);
 }
 // chunk-format engine: one instantiation per (epilogue class, rows per lane, ghost columns); TMA ring of 2 tiles
@@ -1532,7 +1534,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
   ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->full_smooth = c->full_smooth; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
-  ch->kernel = c->kernel; ch->wt_format = c->wt_format; ch->fmt_split = c->fmt_split; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+  ch->kernel = c->kernel; ch->wt_format = c->wt_format; ch->fmt_split = c->fmt_split; ch->engine = c->engine; ch->sv_pf = c->sv_pf; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
   std::vector<Reader> rd;
   for (int p = 0; p < P; ++p) rd.emplace_back(blobs[p]);
   for (int l = LA; l <= NL; ++l) {
@@ -2856,6 +2858,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
     if (value != 0 && value != 1) return fail(2, "engine must be 0 (TMA ring) or 1 (direct)");
     c->engine = (int)value;
   }
+  else if (k == "sv_pf") c->sv_pf = value != 0;
   else if (k == "wt_stages") {
     if (value != 2) return fail(2, "wt_stages: only the 2-deep ring is compiled in (3 and 4 deep measured slower: 2.79 / 2.91 / 3.96 ms)");
     c->wt_stages = (int)value;
@@ -2885,7 +2888,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
     Ctx *ch = c->child.get();
-    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->sv_pf = c->sv_pf; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
     ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   }
   return 0;
