@@ -76,6 +76,9 @@ def make_problem(args):
     return A, opts, name
 
 
+DEFAULT_P2P = "0"   # the library's default ghost exchange (pflare_b200_set_option "p2p")
+
+
 def cache_dir():
     for d in (os.environ.get("PFLARE_BENCH_CACHE"), "/dev/shm", "/tmp"):
         if d and os.path.isdir(d) and os.access(d, os.W_OK):
@@ -464,7 +467,7 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(name, A, H),
             "details": {"streamed_GB_per_cycle": job_bytes / 1e9, "device_bytes": job_dev,
-                        "partition": "1 GPU" if world == 1 else "%d ranks, contiguous row blocks (PETSc MPIAIJ ownership), ghost exchange = %s, levels >= %d agglomerated on rank 0" % (world, "peer-memory push (CUDA IPC)" if any(o.startswith("p2p=1") for o in args.opt) else "NCCL send/recv", l_agg),
+                        "partition": "1 GPU" if world == 1 else "%d ranks, contiguous row blocks (PETSc MPIAIJ ownership), ghost exchange = %s, levels >= %d agglomerated on rank 0" % (world, {"1": "peer-memory push kernel + acks (CUDA IPC)", "2": "peer-memory push fused into the consuming SpMV kernel (CUDA IPC)"}.get(dict(o.split("=") for o in args.opt if "=" in o).get("p2p", DEFAULT_P2P), "NCCL send/recv"), l_agg),
                         "ghost_bytes_per_cycle": job_ghost, "exchange_groups_per_cycle_rank0": int(st["exchange_groups"]),
                         "library_options": args.opt},
             "roofline": roof, "cpu_baseline": cpu, "parity": parity,

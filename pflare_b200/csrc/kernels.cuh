@@ -82,6 +82,10 @@ struct SpmvOp {
   // peer-memory ghost exchange: before the first ghost read, wait until every source rank has pushed
   // its chunk of THIS exchange instance (ready[q] >= *epoch for the ranks q in srcmask)
   const unsigned *gw_ready; const unsigned *gw_epoch; unsigned gw_srcmask;
+  // fused peer-memory exchange (option p2p=2): the kernel itself first pushes THIS rank's boundary entries of x into
+  // the peers' ghost buffers of this exchange instance (xpush), runs its interior tiles, and only the warp that reaches
+  // a tile >= gw_first (the first tile with ghost columns) waits for the peers' chunks
+  const struct XPush *xpush; int gw_first;
 };
 
 // out[i] (=|+=) alpha * a[i] * (b ? b[i] : 1) / (dv ? dv[i] : 1)
@@ -110,13 +114,85 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// consumer side: called by ONE thread of a CTA (or warp) before its first ghost read
+// Bounded spin: a peer that is legitimately late (still in its setup, or running the agglomerated levels) is waited for;
+// after kSpinTimeoutNs the wait gives up and sets *err, so that a lost peer can never hang the GPU.
+const unsigned long long kSpinTimeoutNs = 120ull * 1000000000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void spin_until(const unsigned *flag, unsigned e, unsigned *err) {
+  unsigned long long t0 = 0;
+  int it = 0;
+  while ((int)(ld_acquire_sys(flag) - e) < 0) {
+    __nanosleep(20);
+    if ((++it & 1023) == 0) {
+      const unsigned long long t = global_ns();
+      if (!t0) t0 = t;
+      else if (t - t0 > kSpinTimeoutNs) { if (err) *err = 1u; break; }
+    }
+  }
+}
+// consumer side: called by ONE thread of a CTA (or warp) before its first ghost read (word 1 of the flag block records a timeout)
 __device__ __forceinline__ void ghost_wait(const unsigned *ready, const unsigned *epoch, unsigned srcmask) {
   if (!ready) return;
   const unsigned e = *epoch;
-  for (unsigned m = srcmask; m; m &= m - 1) {
-    const int q = __ffs(m) - 1;
-    while ((int)(ld_acquire_sys(ready + q) - e) < 0) __nanosleep(20);
+  for (unsigned m = srcmask; m; m &= m - 1) spin_until(ready + (__ffs(m) - 1), e, const_cast<unsigned *>(epoch) + 1);
+}
+
+// ---- fused push (p2p=2).  Flag block of a rank: word 0 = epoch (number of the running cycle), words 32..63 =
+// started[q] (rank q has entered cycle e, i.e. finished reading every ghost buffer of cycle e-1), then ready[inst][q].
+// Every exchange instance owns its own ghost buffer, so inside one cycle nothing is ever overwritten and the only
+// back-pressure needed is the once-per-cycle started[] flag (epoch2_kernel).  Word 1 is set when a bounded spin gave up
+// (a peer never arrived): the result is then wrong, nothing hangs, and the next host-buffer apply reports it.
+struct XPush {
+  int n, nranks, me, inst;
+  const int *idx;                        // [n] positions in x of the entries the peers need
+  const int *send_off;                   // [nranks + 1]
+  const unsigned long long *dst;         // [nranks] my chunk inside peer p's ghost buffer of this instance (my address space)
+  const unsigned long long *peer_flags;  // [nranks] peer p's flag block
+  const unsigned *epoch;                 // my flag block
+  unsigned *done;                        // warp-unit counter of this instance
+  unsigned dstmask;
+};
+// called by every warp of the consuming kernel after pdl_wait(): warp-unit u pushes entries [32u, 32u + 32)
+__device__ __forceinline__ void ghost_push(const XPush *__restrict__ px, const double *__restrict__ x, int gwarp, int nwarps, int lane) {
+  if (!px) return;
+  const int n = px->n;
+  const int units = (n + 31) >> 5;
+  if (gwarp >= units) return;
+  const unsigned e = *px->epoch;
+  unsigned cnt = 0;
+  for (int u = gwarp; u < units; u += nwarps) {
+    const int j = u * 32 + lane;
+    if (j < n) {
+      int p = 0;
+      while (j >= px->send_off[p + 1]) ++p;
+      reinterpret_cast<double *>(px->dst[p])[j - px->send_off[p]] = x[px->idx[j]];
+    }
+    ++cnt;
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned prev = atomicAdd(px->done, cnt);
+    if (prev + cnt == (unsigned)units) {   // last unit: every chunk is written and fenced -> raise the consumers' flags
+      *px->done = 0;
+      __threadfence_system();
+      for (unsigned m = px->dstmask; m; m &= m - 1) {
+        const int p = __ffs(m) - 1;
+        st_release_sys(reinterpret_cast<unsigned *>(px->peer_flags[p]) + 64 + (size_t)px->inst * 32 + px->me, e);
+      }
+    }
+  }
+}
+// lazy consumer gate: armed while the warp has not yet waited for the peers' chunks
+__device__ __forceinline__ void ghost_gate(const SpmvOp &op, bool &armed, int tile, int lane) {
+  if (armed && tile >= op.gw_first) {
+    if (lane == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+    __syncwarp();
+    armed = false;
   }
 }
 
@@ -298,9 +374,46 @@ __global__ void __launch_bounds__(kThreads) spmv_stream_kernel(const SpmvOp op) 
   pdl_wait();
   __shared__ double prod[kTile];
   __shared__ double red[kThreads / 32];
+  ghost_push(op.xpush, op.x, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
   if (threadIdx.x == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
   __syncthreads();
   for (int b = blockIdx.x; b < op.nblk; b += gridDim.x) process_block<kThreads>(op, b, prod, red);
+}
+
+// Rows longer than a warp tile (compact CSR of just those rows, rowmap = their row numbers): one warp per row, the lanes
+// stride the row with four independent 128-entry groups in flight, shuffle reduction, generic epilogue on lane 0.
+__global__ void __launch_bounds__(256) spmv_longrow_kernel(const SpmvOp op) {
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int *__restrict__ rp = op.rp;
+  const int *__restrict__ col = op.col;
+  const double *__restrict__ val = op.val;
+  int r = gw;
+  int p0 = 0, p1 = 0;
+  if (r < op.m) { p0 = rp[r]; p1 = rp[r + 1]; }
+  pdl_wait();
+  if (lane == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+  __syncwarp();
+  for (; r < op.m; r += nw) {
+    const int q0 = p0, q1 = p1 - (op.wlast ? 1 : 0), last = p1 - 1;
+    if (r + nw < op.m) { p0 = rp[r + nw]; p1 = rp[r + nw + 1]; }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = q0 + lane;
+    for (; p + 96 < q1; p += 128) {
+      const int c0 = __ldcs(col + p), c1 = __ldcs(col + p + 32), c2 = __ldcs(col + p + 64), c3 = __ldcs(col + p + 96);
+      const double v0 = __ldcs(val + p), v1 = __ldcs(val + p + 32), v2 = __ldcs(val + p + 64), v3 = __ldcs(val + p + 96);
+      s0 += v0 * gather_x(op, c0); s1 += v1 * gather_x(op, c1); s2 += v2 * gather_x(op, c2); s3 += v3 * gather_x(op, c3);
+    }
+    for (; p < q1; p += 32) s0 += __ldcs(val + p) * gather_x(op, __ldcs(col + p));
+    double sum = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) {
+      const double xw = op.wlast ? val[last] * gather_x(op, col[last]) : 0.0;
+      row_epilogue(op, op.rowmap ? op.rowmap[r] : r, sum, xw);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -400,7 +513,8 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
   if (lane == 0)
     for (int j = 0; j < STAGES && j < my; ++j) issue(j);   // matrix data only: legal before pdl_wait
   pdl_wait();   // from here on the vectors written by the previous kernels are read
-  if (GHOST && lane == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+  if (GHOST) ghost_push(op.xpush, op.x, first, nwarps, lane);
+  bool garmed = GHOST && op.gw_ready != nullptr;
   __syncwarp();
 
   const double *__restrict__ xv = op.x;
@@ -412,6 +526,7 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wt_kernel(const SpmvOp op) {
   // stage A of tile j
   auto stage_a = [&](int j) {
     const int slot = j % STAGES;
+    if (GHOST) ghost_gate(op, garmed, first + j * nwarps, lane);
     mbar_wait(&full[w][slot], (uint32_t)((j / STAGES) & 1));
     dnx = sdesc[w][slot];
     const int nslots = (dnx.geom & 0xff) * KP;
@@ -557,7 +672,8 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wc_kernel(const SpmvOp op) {
   if (lane == 0)
     for (int j = 0; j < STAGES && j < my; ++j) issue(j);   // matrix data only: legal before pdl_wait
   pdl_wait();   // from here on the vectors written by the previous kernels are read
-  if (GHOST && lane == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
+  if (GHOST) ghost_push(op.xpush, op.x, first, nwarps, lane);
+  bool garmed = GHOST && op.gw_ready != nullptr;
   __syncwarp();
 
   const double *__restrict__ xv = op.x;
@@ -569,6 +685,7 @@ __global__ void __launch_bounds__(NW * 32, 2) spmv_wc_kernel(const SpmvOp op) {
   // stage A of tile j
   auto stage_a = [&](int j) {
     const int slot = j % STAGES;
+    if (GHOST) ghost_gate(op, garmed, first + j * nwarps, lane);
     mbar_wait(&full[w][slot], (uint32_t)((j / STAGES) & 1));
     dnx = sdesc[w][slot];
     const int *col_s = reinterpret_cast<const int *>(wbase + slot * kWcStageBytes + dnx.geom * 256);
@@ -701,7 +818,7 @@ __global__ void __launch_bounds__(256, PF ? 3 : 4) spmv_sv_kernel(const SpmvOp o
 #pragma unroll
     for (int k = 0; k < NSLOT; ++k) cn[k] = (k < nsl) ? __ldcs(cg + k * 32 + lane) : 0;
   }
-  bool waited = false;
+  bool waited = false, garmed = GHOST && op.gw_ready != nullptr;
   for (; t < op.nwt; t += nwarps) {
     const WtDesc d = dn;
     if (PF) {
@@ -737,9 +854,11 @@ __global__ void __launch_bounds__(256, PF ? 3 : 4) spmv_sv_kernel(const SpmvOp o
     unsigned hd[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) hd[s] = (s < ns) ? __ldg(heads + s) : 0u;
-    if (!waited) { pdl_wait(); waited = true; }   // from here on the vectors written by the previous kernels are read
-    if (GHOST && lane == 0 && t == gw) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
-    if (GHOST) __syncwarp();
+    if (!waited) {   // from here on the vectors written by the previous kernels are read
+      pdl_wait(); waited = true;
+      if (GHOST) ghost_push(op.xpush, op.x, gw, nwarps, lane);
+    }
+    if (GHOST) ghost_gate(op, garmed, t, lane);
     // gathers
     double xr[NSLOT];
 #pragma unroll
@@ -796,7 +915,10 @@ __global__ void __launch_bounds__(256, PF ? 3 : 4) spmv_sv_kernel(const SpmvOp o
       }
     }
   }
-  if (!waited) pdl_wait();
+  if (!waited) {   // a warp without tiles still takes part in the push
+    pdl_wait();
+    if (GHOST) ghost_push(op.xpush, op.x, gw, nwarps, lane);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -858,6 +980,7 @@ __global__ void __launch_bounds__(NT) spmv_tma_kernel(const SpmvOp op) {
     for (int j = 0; j < STAGES - 1 && j < my_tiles; ++j) issue(j);   // matrix data only: legal before pdl_wait
   }
   pdl_wait();
+  ghost_push(op.xpush, op.x, (blockIdx.x * NT + tid) >> 5, (gridDim.x * NT) >> 5, tid & 31);
   if (tid == 0) ghost_wait(op.gw_ready, op.gw_epoch, op.gw_srcmask);
   __syncthreads();
 
@@ -1086,6 +1209,26 @@ __global__ void __launch_bounds__(kThreads) push_kernel(const PushOp o) {
       }
     }
   }
+}
+
+// p2p=2: the push on its own (the consuming operator has no rows on this rank, or an in-process rank group on ONE stream,
+// where a consumer that waited inside its kernel for a later launch would never return)
+__global__ void __launch_bounds__(kThreads) push2_kernel(const XPush *px, const double *x) {
+  pdl_launch_dependents();
+  pdl_wait();
+  ghost_push(px, x, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, threadIdx.x & 31);
+}
+// p2p=2: enter cycle e = ++epoch, tell the ranks in `raise` (they push to me: everything this rank read in cycle e-1 is
+// finished, stream order), and wait until the ranks in `wait` (I push to them) have entered cycle e as well
+__global__ void epoch2_kernel(unsigned *flags, const unsigned long long *peer_flags, int me, unsigned raise, unsigned wait) {
+  const unsigned e = *flags + 1;
+  *flags = e;
+  __threadfence_system();
+  for (unsigned m = raise; m; m &= m - 1) {
+    const int p = __ffs(m) - 1;
+    st_release_sys(reinterpret_cast<unsigned *>(peer_flags[p]) + 32 + me, e);
+  }
+  for (unsigned m = wait; m; m &= m - 1) spin_until(flags + 32 + (__ffs(m) - 1), e, flags + 1);
 }
 
 // consumer -> producers: "I have finished reading the ghosts of instance inst" (runs after the SpMV)

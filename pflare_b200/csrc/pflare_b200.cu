@@ -183,6 +183,7 @@ struct Op {
   const double *xsrc = nullptr;
   int inst = -1, ack_inst = -1, ack_delta = 0;   // peer-memory exchange instance (and the one whose acks it waits for)
   bool async = false;           // OPK_XCHG: run on the side stream, joined by the following OPK_XWAIT
+  bool push_here = false;       // p2p=2: the consuming SpMV kernel of this rank pushes the entries itself (no launch for the exchange)
   int level = 0;
   int tag = 0;  // 1 restrict, 2 coarse, 3 A_fc(+W), 4 A_ff residual, 5 inverse, 6 elementwise, 7 fused local smooth, 8 A_cf, 9 A_cc, 10 exchange, 11 dense tail
   double bytes = 0, nnz = 0;
@@ -255,8 +256,18 @@ struct Ctx {
   int overlap = 1;       // NCCL exchange on a side stream, overlapped with the interior tiles of the SpMV
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int p2p = 0;   // 1: peer-memory push/flag exchange (CUDA IPC); 0: NCCL send/recv (measured faster in round 1)
+  int p2p = 0;   // 0: NCCL send/recv; 1: peer-memory push kernel + flags + acks (CUDA IPC); 2: push fused into the consuming SpMV kernel,
+                 //    one ghost buffer per exchange instance, one started[] flag per cycle instead of acks
   bool p2p_ready = false;
+  bool fused_push() const { return p2p == 2 && p2p_ready; }
+  std::vector<int> inst_plan;            // p2p=2: plan of every exchange instance of the cycle program
+  std::vector<int> inst_plan_built;      //        ... the layout arena2 was built for
+  char *arena2 = nullptr;                //        ghost buffers of the instances (mapped by every peer)
+  std::vector<int64_t> inst_off;         //        byte offset of instance i inside arena2
+  std::vector<void *> peer_arena2;
+  std::vector<bool> peer_ipc2;
+  XPush *d_xpush = nullptr;              //        [n_inst] descriptors
+  unsigned all_dst = 0, all_src = 0;     //        union of the plans' masks
   char *arena = nullptr; size_t arena_bytes = 0;
   std::vector<void *> peer_arena;        // [P] peers' arenas in my address space (IPC-mapped or same process)
   std::vector<bool> peer_ipc;
@@ -489,6 +500,7 @@ double spmv_bytes(const DevCSR &A, int n_aux_reads, int w) {
 }
 
 // ------------------------------------------------------------------ program construction
+bool op_is_empty(const Op &o);
 struct Builder {
   Ctx *c;
   std::vector<Op> *out;
@@ -562,6 +574,19 @@ struct Builder {
       o.s.gw_epoch = c->flags();
       o.s.gw_srcmask = A.xp->srcmask;
     }
+    if (p2p && c->p2p == 2) {
+      // fused exchange: xg / xpush are patched by setup_fused_push() once the instance buffers exist
+      o.inst = inst;
+      o.s.gw_first = A.wt ? A.nwt_int : 0;
+      o.push_here = !c->cluster && !op_is_empty(o);
+      (*out)[out->size() - 1].push_here = o.push_here;   // the OPK_XCHG pushed above
+      int pid = 0;
+      for (const DevPlan &D : c->plans) { if (&D == A.xp) break; ++pid; }
+      c->inst_plan.push_back(pid);
+      out->push_back(o);
+      push_long_rows(o, A);
+      return;
+    }
     out->push_back(o);
     push_long_rows(o, A);
     if (p2p) {   // tell the producers that this rank is done with the ghosts of this instance
@@ -580,7 +605,8 @@ struct Builder {
     l.s.rp = A.lrp; l.s.col = A.lcol; l.s.val = A.lval; l.s.rowmap = A.lrow;
     l.s.m = A.nlong; l.s.nblk = A.nlong; l.s.blk = A.lblk; l.s.ntiles = A.nlong;
     l.s.epi = EPI_GENERIC;
-    l.s.gw_ready = nullptr;   // the main op already waited for (and acknowledges) the ghosts
+    if (c->p2p != 2) l.s.gw_ready = nullptr;   // p2p=1: the main op already waited for (and acknowledges) the ghosts
+    l.s.xpush = nullptr; l.s.gw_first = 0; l.push_here = false;   // p2p=2: waits itself (own buffer per instance, no ack), never pushes
     l.bytes = 0; l.nnz = 0;
     out->push_back(l);
   }
@@ -1059,6 +1085,11 @@ int launch_op(Ctx *c, const Op &o, cudaStream_t st, bool dry = false) {
       rc = launch_wt(c, o.s, st, dry);
     } else if (c->kernel == 1 && o.s.tiles) {
       rc = launch_r1(c, o.s, st, dry);
+    } else if (o.s.rowmap) {   // the rows longer than a warp tile: one warp per row
+      if (dry) return 0;
+      int grid = std::min((o.s.m + 7) / 8, c->num_sms * 8);
+      if (c->max_ctas > 0) grid = std::min(grid, c->max_ctas);
+      CUDA_TRY(launch_k(c->pdl != 0, spmv_longrow_kernel, grid, 256, 0, st, o.s));
     } else {
       if (dry) return 0;
       int grid = std::min(o.s.nblk, c->num_sms * 8 * 4);
@@ -1128,7 +1159,17 @@ int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op
         if (rc) return rc;
       }
     } else if (kind == OPK_EPOCH) {
-      for (int r = 0; r < nr; ++r) epoch_kernel<<<1, 1, 0, st>>>(R[r]->flags());
+      for (int r = 0; r < nr; ++r) {
+        Ctx *c = R[r];
+        if (c->p2p == 2) {
+          // enter the cycle, tell the ranks that push to me, and (one process per GPU) wait until the ranks I push to have
+          // entered it too: their ghost buffers of the previous cycle are then free.  An in-process group runs on one
+          // stream: all epoch kernels are queued before the first push, nothing to wait for.
+          epoch2_kernel<<<1, 1, 0, st>>>(c->flags(), c->d_peer_flags, c->rank, c->all_src, nr > 1 ? 0u : c->all_dst);
+        } else {
+          epoch_kernel<<<1, 1, 0, st>>>(c->flags());
+        }
+      }
       CUDA_TRY(cudaGetLastError());
     } else if (kind == OPK_ACK) {
       for (int r = 0; r < nr; ++r) {
@@ -1137,6 +1178,17 @@ int exec_ops(const std::vector<Ctx *> &R, const std::vector<const std::vector<Op
         ack_kernel<<<1, 1, 0, st>>>(R[r]->d_peer_flags, R[r]->flags(), kMaxInst, o.inst, R[r]->rank, o.xp->srcmask);
       }
       CUDA_TRY(cudaGetLastError());
+    } else if (kind == OPK_XCHG && (*progs[0])[i].inst >= 0 && R[0]->p2p == 2) {
+      // fused exchange: normally no launch at all (the consuming kernel pushes); a stand-alone push only where this
+      // rank's consumer has no rows, and for in-process groups (one stream: a consumer must never wait for a later launch)
+      for (int r = 0; r < nr; ++r) {
+        Ctx *c = R[r];
+        const Op &o = (*progs[r])[i];
+        if (o.push_here || !o.xp->dstmask) continue;
+        const int units = (o.xp->plan.n_send() + 31) / 32;
+        const int grid = std::max(1, std::min((units + 7) / 8, 64));
+        CUDA_TRY(launch_k(c->pdl != 0, push2_kernel, grid, kThreads, 0, st, (const XPush *)(c->d_xpush + o.inst), o.xsrc));
+      }
     } else if (kind == OPK_XCHG && (*progs[0])[i].inst >= 0) {
       // peer-memory exchange: every rank pushes its chunks straight into the consumers' ghost buffers and
       // raises their flags; the consumers' SpMV kernels wait on the flags (kernels.cuh: push_kernel / ghost_wait)
@@ -1295,6 +1347,8 @@ int build_graph(Ctx *c) {
   return 0;
 }
 
+int setup_fused_push(Ctx *c);
+
 int build_program(Ctx *c) {
   c->prog.clear();
   c->tail_levels = 0;
@@ -1307,6 +1361,7 @@ int build_program(Ctx *c) {
   B.io = c->io_fused;
   c->n_head = 0; c->tail_begin = -1;
   c->n_inst = 0;
+  c->inst_plan.clear();
   for (DevPlan &D : c->plans) D.first_inst = D.last_inst = -1;
   if (c->p2p_ready) { Op e; e.kind = OPK_EPOCH; e.tag = 10; c->prog.push_back(e); }
   // dense collapsed tail (serial contexts): the longest suffix of levels with <= dense_rows rows
@@ -1423,6 +1478,10 @@ int build_program(Ctx *c) {
     c->tail_levels = NL - ldense + 1;
   } else {
     c->dense_prog.clear(); c->dense_level = 0; c->dense_n = 0;
+  }
+  if (c->fused_push()) {
+    int rc = setup_fused_push(c);
+    if (rc) return rc;
   }
   if (c->p2p_ready) {
     if (c->n_inst > kMaxInst) return fail(25, "the cycle needs %d ghost exchanges, the flag block holds %d: set option p2p=0", c->n_inst, kMaxInst);
@@ -1684,6 +1743,87 @@ int setup_p2p(Ctx *c) {
   return 0;
 }
 
+// p2p=2, after the cycle program assigned the exchange instances: one ghost buffer per instance (arena2, mapped by the
+// peers like the flag arena), the per-instance destination table and the XPush descriptors; then the program's ops get
+// their buffer / descriptor pointers.  Collective (every rank builds the same instance list); skipped when the instance
+// layout is the one arena2 was built for (an option change that keeps the op list's exchanges).
+int setup_fused_push(Ctx *c) {
+  const int P = c->nranks, NI = c->n_inst;
+  int rc;
+  if (NI > kMaxInst) return fail(25, "the cycle needs %d ghost exchanges, the flag block holds %d: set option p2p=0", NI, kMaxInst);
+  if (!c->arena2 || c->inst_plan != c->inst_plan_built) {
+    for (size_t p = 0; p < c->peer_arena2.size(); ++p)
+      if (c->peer_ipc2[p] && c->peer_arena2[p]) cudaIpcCloseMemHandle(c->peer_arena2[p]);
+    c->peer_arena2.clear(); c->peer_ipc2.clear();
+    c->inst_off.assign((size_t)NI + 1, 0);
+    for (int i = 0; i < NI; ++i)
+      c->inst_off[(size_t)i + 1] = c->inst_off[(size_t)i] + (int64_t)((((size_t)c->plans[(size_t)c->inst_plan[(size_t)i]].plan.n_ghost * 8) + 255) & ~(size_t)255);
+    if ((rc = dev_alloc(c, &c->arena2, (size_t)c->inst_off[(size_t)NI] + 256))) return rc;
+    CUDA_TRY(cudaMemset(c->arena2, 0, (size_t)c->inst_off[(size_t)NI] + 256));
+    struct Hello { int32_t same_process_tag; int32_t n_inst; uint64_t raw; cudaIpcMemHandle_t ipc; };
+    Hello me{};
+    me.same_process_tag = c->cluster ? 1 : 0;
+    me.n_inst = NI;
+    me.raw = (uint64_t)(uintptr_t)c->arena2;
+    if (!c->cluster) CUDA_TRY(cudaIpcGetMemHandle(&me.ipc, c->arena2));
+    std::vector<std::vector<char>> out((size_t)P), in;
+    for (int p = 0; p < P; ++p) {
+      Writer w;
+      w.put(me);
+      for (int i = 0; i < NI; ++i)   // where p's chunk of instance i lands in MY arena2
+        w.put<int64_t>(c->inst_off[(size_t)i] + 8 * (int64_t)c->plans[(size_t)c->inst_plan[(size_t)i]].plan.recv_off[p]);
+      out[p] = std::move(w.buf);
+    }
+    std::string err;
+    if (exchange_blobs(c->hostcomm.get(), out, &in, &err)) return fail(22, "peer-memory setup exchange failed: %s", err.c_str());
+    c->peer_arena2.assign((size_t)P, nullptr);
+    c->peer_ipc2.assign((size_t)P, false);
+    std::vector<unsigned long long> dst((size_t)std::max(NI, 1) * P, 0);
+    for (int p = 0; p < P; ++p) {
+      Reader r(in[p]);
+      const Hello h = r.get<Hello>();
+      if (!r.ok || h.n_inst != NI) return fail(24, "rank %d built a cycle with %d ghost exchanges, this rank %d", p, r.ok ? h.n_inst : -1, NI);
+      if (p == c->rank) c->peer_arena2[p] = c->arena2;
+      else if (h.same_process_tag) c->peer_arena2[p] = (void *)(uintptr_t)h.raw;
+      else {
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(26, "cudaIpcOpenMemHandle(rank %d): %s -- set option p2p=0 to use NCCL", p, cudaGetErrorString(e));
+        c->peer_arena2[p] = ptr; c->peer_ipc2[p] = true;
+      }
+      for (int i = 0; i < NI; ++i) {
+        const int64_t off = r.get<int64_t>();
+        dst[(size_t)i * P + p] = (unsigned long long)(uintptr_t)c->peer_arena2[p] + (unsigned long long)off;
+      }
+      if (!r.ok) return fail(24, "malformed peer-memory hello from rank %d", p);
+    }
+    unsigned long long *d_dst = nullptr;
+    if ((rc = dev_upload(c, &d_dst, dst))) return rc;
+    std::vector<XPush> xp((size_t)std::max(NI, 1));
+    for (int i = 0; i < NI; ++i) {
+      const DevPlan &D = c->plans[(size_t)c->inst_plan[(size_t)i]];
+      XPush &x = xp[(size_t)i];
+      x.n = D.plan.n_send(); x.nranks = P; x.me = c->rank; x.inst = i;
+      x.idx = D.d_send_idx; x.send_off = D.d_send_off; x.dst = d_dst + (size_t)i * P;
+      x.peer_flags = c->d_peer_flags; x.epoch = c->flags(); x.done = c->d_done + i; x.dstmask = D.dstmask;
+    }
+    if ((rc = dev_upload(c, &c->d_xpush, xp))) return rc;
+    c->inst_plan_built = c->inst_plan;
+    c->all_dst = c->all_src = 0;
+    for (const DevPlan &D : c->plans) { c->all_dst |= D.dstmask; c->all_src |= D.srcmask; }
+  }
+  auto patch = [&](std::vector<Op> &ops) {
+    for (Op &o : ops)
+      if (o.kind == OPK_SPMV && o.inst >= 0) {
+        o.s.xg = reinterpret_cast<const double *>(c->arena2 + c->inst_off[(size_t)o.inst]);
+        o.s.xpush = o.push_here ? c->d_xpush + o.inst : nullptr;
+      }
+  };
+  patch(c->prog);
+  patch(c->dense_prog);
+  return 0;
+}
+
 void destroy_ctx(Ctx *c);
 
 // Everything a previous finalize_setup built on the device (operators, vectors, plans, dense tail, graph, the
@@ -1698,10 +1838,14 @@ void release_device_state(Ctx *c) {
     if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
     for (size_t p = 0; p < c->peer_arena.size(); ++p)
       if (c->peer_ipc[p] && c->peer_arena[p]) cudaIpcCloseMemHandle(c->peer_arena[p]);
+    for (size_t p = 0; p < c->peer_arena2.size(); ++p)
+      if (c->peer_ipc2[p] && c->peer_arena2[p]) cudaIpcCloseMemHandle(c->peer_arena2[p]);
     for (void *p : c->allocs) cudaFree(p);
   }
   if (c->child) destroy_ctx(c->child.release());
   c->peer_arena.clear(); c->peer_ipc.clear();
+  c->peer_arena2.clear(); c->peer_ipc2.clear(); c->arena2 = nullptr; c->d_xpush = nullptr;
+  c->inst_plan.clear(); c->inst_plan_built.clear(); c->inst_off.clear();
   c->allocs.clear(); c->dev_bytes = 0;
   c->plans.clear(); c->prog.clear(); c->dense_prog.clear();
   c->dense_T = nullptr; c->dense_cap = 0; c->dense_built = false; c->dense_level = 0; c->dense_n = 0;
@@ -2103,7 +2247,7 @@ int finalize_ctx(Ctx *c) {
         if ((rc = dev_alloc(c, &D.d_sendbuf, (size_t)D.plan.n_send()))) return rc;
         D.d_xg = reinterpret_cast<double *>(c->arena + D.xg_off);
       }
-      if (c->p2p && P <= 32) {
+      if (c->p2p && P <= 32) {   // p2p = 1 and 2 share the flag arena; 2 adds the per-instance buffers after the program is built
         if ((rc = setup_p2p(c))) return rc;
       }
     }
@@ -2207,6 +2351,11 @@ int apply_ctx(Ctx *c, const double *b, double *x, int on_device) {
   if (!on_device) {
     CUDA_TRY(cudaMemcpyAsync(x, c->io_x, (size_t)L1.n * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->p2p_ready) {   // word 1 of the flag block: a bounded wait for a peer's ghosts gave up (kernels.cuh: spin_until)
+      unsigned tmo = 0;
+      CUDA_TRY(cudaMemcpy(&tmo, c->flags() + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));
+      if (tmo) return fail(27, "peer-memory ghost exchange timed out waiting for another rank: the result of this apply is not valid");
+    }
   }
   return 0;
 }
@@ -2883,7 +3032,8 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else if (k == "overlap") c->overlap = value != 0;
   else if (k == "p2p") {
     if (c->finalized || c->planned) return fail(2, "p2p must be set before finalize_setup");
-    c->p2p = value != 0;
+    if (value != 0 && value != 1 && value != 2) return fail(2, "p2p: 0 (NCCL send/recv), 1 (push kernel + acks) or 2 (push fused into the consuming kernel)");
+    c->p2p = (int)value;
   }
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
@@ -2925,6 +3075,8 @@ void destroy_ctx(Ctx *c) {
     if (c->child) { destroy_ctx(c->child.release()); }
     for (size_t p = 0; p < c->peer_arena.size(); ++p)
       if (c->peer_ipc[p] && c->peer_arena[p]) cudaIpcCloseMemHandle(c->peer_arena[p]);
+    for (size_t p = 0; p < c->peer_arena2.size(); ++p)
+      if (c->peer_ipc2[p] && c->peer_arena2[p]) cudaIpcCloseMemHandle(c->peer_arena2[p]);
     for (void *p : c->allocs) cudaFree(p);
     if (c->ksp_hdots) cudaFreeHost(c->ksp_hdots);
     if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }

@@ -41,8 +41,8 @@ def main():
         xo = hiergen.feed(H, oracle.OracleAIR(H.no_levels)).apply(b)
         parts = hiergen.partition(H, world)
         rg = parts[0].rangesV[0]
-        # p2p=1: CUDA-IPC peer-memory exchange; p2p=0: NCCL send/recv, with (overlap=1) or without the side-stream split phase
-        for agg_rows, p2p, overlap in ((0, 1, 1), (600, 1, 1), (600, 0, 1), (0, 0, 1), (600, 0, 0)):
+        # p2p=1: CUDA-IPC peer-memory exchange (push kernel + acks); p2p=2: push fused into the consuming SpMV kernel; p2p=0: NCCL send/recv, with (overlap=1) or without the side-stream split phase
+        for agg_rows, p2p, overlap in ((0, 2, 1), (600, 2, 1), (0, 1, 1), (600, 1, 1), (600, 0, 1), (0, 0, 1), (600, 0, 0)):
             pc = pflare_b200.PC(rank=rank, nranks=world, unique_id=fresh_uid(), device=local).setType("air").setHierarchy(parts[rank])
             pc.setOption("agg_rows", agg_rows)
             pc.setOption("p2p", p2p)

@@ -50,7 +50,7 @@ def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
     b = cases.rhs(A.shape[0])
     xo = _oracle(H).apply(b)
     for agg_rows in (0, 600, 10 ** 9):       # fully distributed | coarse levels on rank 0 | everything below level 1 on rank 0
-        x, (l_agg, stats) = _cluster_apply(H, nranks, b, agg_rows=agg_rows, dense_rows=0 if nranks == 3 else 4096, p2p=1 if nranks == 4 else 0)
+        x, (l_agg, stats) = _cluster_apply(H, nranks, b, agg_rows=agg_rows, dense_rows=0 if nranks == 3 else 4096, p2p={4: 1, 2: 2}.get(nranks, 0))
         assert cases.rel_l2(x, xo) <= TOL, (name, nranks, agg_rows)
         if agg_rows == 0:
             assert l_agg == H.no_levels + 1
@@ -60,7 +60,8 @@ def test_partitioned_vcycle_matches_serial_oracle(built_libs, name, nranks):
 
 
 @pytest.mark.parametrize("opts", [dict(graph=0), dict(kernel=0), dict(fuse=0), dict(kernel=1), dict(dense_rows=0), dict(pdl=0), dict(p2p=1), dict(p2p=1, graph=0), dict(overlap=0), dict(overlap=0, graph=0),
-                                  dict(epi_classes=0), dict(engine=0, p2p=1), dict(max_ctas=1), dict(kernel=1, p2p=1)], ids=str)
+                                  dict(epi_classes=0), dict(engine=0, p2p=1), dict(max_ctas=1), dict(kernel=1, p2p=1),
+                                  dict(p2p=2), dict(p2p=2, graph=0), dict(p2p=2, engine=0), dict(p2p=2, kernel=1), dict(p2p=2, kernel=0), dict(p2p=2, max_ctas=1), dict(p2p=2, fuse=0)], ids=str)
 def test_partitioned_execution_modes(built_libs, opts):
     A, H = cases.build("fd2d_64")
     b = cases.rhs(A.shape[0], seed=3)
@@ -85,6 +86,23 @@ def test_repeated_applies_reuse_ghost_buffers_safely(built_libs):
     cl.close()
 
 
+def test_repeated_applies_with_the_fused_push(built_libs):
+    """p2p=2: one ghost buffer per exchange instance, ready[] flags per instance and one started[] flag per cycle (no acks);
+    in an in-process group the pushes run as stand-alone launches of the same device code (kernels.cuh: ghost_push)."""
+    A, H = cases.build("fd2d_mf_newton")
+    parts = hiergen.partition(H, 4)
+    cl = pflare_b200.ClusterAIR(H.no_levels, 4)
+    cl.set_option("agg_rows", 300)
+    cl.set_option("p2p", 2)
+    cl.upload(parts)
+    O = _oracle(H)
+    for seed in range(5):
+        b = cases.rhs(A.shape[0], seed=seed)
+        xs = cl.apply(hiergen.scatter_vector(b, parts[0].rangesV[0]))
+        assert cases.rel_l2(np.concatenate(xs), O.apply(b)) <= TOL
+    cl.close()
+
+
 def test_more_ranks_than_coarse_rows(built_libs):
     """Ranks that own zero rows on the coarse levels (PETSc allows empty ranks; the reference's processor
     agglomeration produces them on purpose, src/AIR_Data_Type.F90:56-76)."""
@@ -92,8 +110,9 @@ def test_more_ranks_than_coarse_rows(built_libs):
     b = cases.rhs(A.shape[0])
     xo = _oracle(H).apply(b)
     for agg_rows in (0, 100):
-        x, _ = _cluster_apply(H, 7, b, agg_rows=agg_rows)
-        assert cases.rel_l2(x, xo) <= TOL
+        for p2p in (0, 2):
+            x, _ = _cluster_apply(H, 7, b, agg_rows=agg_rows, p2p=p2p)
+            assert cases.rel_l2(x, xo) <= TOL
 
 
 @pytest.mark.parametrize("name", ["inv_newton_10_o50", "inv_arnoldi_asm", "inv_neumann_mf", "inv_power_mf"])
