@@ -76,7 +76,7 @@ def make_problem(args):
     return A, opts, name
 
 
-DEFAULT_P2P = "0"   # the library's default ghost exchange (pflare_b200_set_option "p2p")
+DEFAULT_P2P = "2"   # the library's default ghost exchange (pflare_b200_set_option "p2p")
 
 
 def cache_dir():

@@ -126,6 +126,7 @@ __device__ __forceinline__ void spin_until(const unsigned *flag, unsigned e, uns
   unsigned long long t0 = 0;
   int it = 0;
   while ((int)(ld_acquire_sys(flag) - e) < 0) {
+    if (err && *reinterpret_cast<volatile unsigned *>(err)) break;   // an earlier wait already gave up: fall through, do not wait again
     __nanosleep(20);
     if ((++it & 1023) == 0) {
       const unsigned long long t = global_ns();

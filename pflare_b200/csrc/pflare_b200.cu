@@ -256,7 +256,7 @@ struct Ctx {
   int overlap = 1;       // NCCL exchange on a side stream, overlapped with the interior tiles of the SpMV
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int p2p = 0;   // 0: NCCL send/recv; 1: peer-memory push kernel + flags + acks (CUDA IPC); 2: push fused into the consuming SpMV kernel,
+  int p2p = 2;   // 0: NCCL send/recv; 1: peer-memory push kernel + flags + acks (CUDA IPC); 2: push fused into the consuming SpMV kernel,
                  //    one ghost buffer per exchange instance, one started[] flag per cycle instead of acks
   bool p2p_ready = false;
   bool fused_push() const { return p2p == 2 && p2p_ready; }
@@ -2929,7 +2929,9 @@ static void collect_stats(Ctx *c, double *v) {
     v[1] += (o.kind == OPK_XCHG || o.kind == OPK_GATHER0 || o.kind == OPK_SCATTER0 || (o.kind == OPK_EW && o.user)) ? 0.0 : o.bytes;   // exchanges and the exit scatter are not in the SURVEY.md 8d model
     v[2] += o.nnz;
     if (o.kind == OPK_SPMV || o.kind == OPK_EW) v[5] = std::max(v[5], o.bytes);
-    if (!op_is_empty(o) && o.kind != OPK_CHILD) ++nk;
+    const bool silent = o.kind == OPK_CHILD || o.kind == OPK_XWAIT ||
+                        (o.kind == OPK_XCHG && c->p2p == 2 && o.inst >= 0 && (o.push_here || !o.xp->dstmask));   // fused push: no launch of its own
+    if (!op_is_empty(o) && !silent) ++nk;
   }
   v[0] += nk;
   v[3] += c->dev_bytes;
