@@ -23,7 +23,10 @@ NOT_SPMV = ("elementwise/permute", "dense tail", "exchange", "coarse-child")
 
 
 def read_report(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):   # `ncu -i rep --page raw --csv` saved on the GPU box (the report itself can be too big to travel)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
 
