@@ -53,6 +53,32 @@ def main():
                 worst = max(worst, err)
             dist.barrier()
             pc.destroy()
+    # outer Krylov method across the ranks (pflare_b200_ksp_solve: the cycle's fused exchange, the system matrix over NCCL
+    # send/recv, the Gram-Schmidt scalars through ncclAllReduce): iteration count equal (+-1) to a host GMRES around the oracle
+    from krylov import gmres
+    from hiergen.partition import _split_cols
+    for name, rtol, p2p in (("fd2d_64", 1e-8, 2), ("fd2d_mf_newton", 1e-8, 0)):
+        A, H = cases.build(name)
+        n = A.shape[0]
+        parts = hiergen.partition(H, world)
+        rg = parts[0].rangesV[0]
+        O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))
+        _, its_cpu, conv_cpu = gmres(A, np.zeros(n), np.ones(n), O.apply, rtol=rtol, side="right")
+        d = pflare_b200.DeviceAIR(H.no_levels, rank=rank, nranks=world, unique_id=fresh_uid(), device=local)
+        d.set_option("p2p", p2p)
+        dg, od, ga = _split_cols(A.tocsr()[rg[rank]:rg[rank + 1]], rg[rank], rg[rank + 1])
+        d.ksp_set_operator(dg, od, ga, cstart=rg[rank])
+        parts[rank].feed(d)
+        xl, its, conv, rn = d.ksp_solve(np.zeros(rg[rank + 1] - rg[rank]), np.ones(rg[rank + 1] - rg[rank]), ksp_type="gmres", side="right", rtol=rtol)
+        pieces = [None] * world
+        dist.all_gather_object(pieces, xl)
+        x = np.concatenate(pieces)
+        res = np.linalg.norm(A @ x) / np.linalg.norm(A @ np.ones(n))
+        if rank == 0:
+            print("ksp %s: its %d (host around the oracle: %d), converged %s, relative residual %.2e" % (name, its, its_cpu, conv, res))
+        assert conv and conv_cpu and abs(its - its_cpu) <= 1 and res <= 10 * rtol, (name, its, its_cpu, res)
+        dist.barrier()
+        d.close()
     t = torch.tensor([worst], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
