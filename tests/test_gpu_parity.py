@@ -292,3 +292,23 @@ def test_medium_size_parity_and_linearity(built_libs):
     st = d.stats()
     assert st["kernel_launches"] > 0 and st["algorithmic_bytes"] > 12 * st["nnz_per_cycle"]
     d.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["L", "U"])
+def test_ilu_factor_pflareinv_of_the_reference_fixture(built_libs, which):
+    """BASELINE.json configs[4] (tests/ilu_factors.c): PCPFLAREINV (Newton basis, matrix-free, order 6) on the ParILU(0) factors of
+    the reference's data fixture mat_stream_2364: the apply matches the oracle / the frozen vector to 1e-12, and the Richardson solve
+    the reference test runs (rtol 1e-6, max_it 2000) converges on the device in the same number of iterations."""
+    F, H, g = cases.ilu_factor_case(which)
+    n = F.shape[0]
+    d = pflare_b200.DeviceAIR(1)
+    d.ksp_set_operator(F)
+    hiergen.feed(H, d)
+    y = d.inv_apply(1, pflare_b200.INV_AFF, g["b"])
+    assert cases.rel_l2(y, g["apply"]) <= TOL
+    assert cases.rel_l2(y, _oracle(H).inv_apply(1, oracle.INV_AFF, g["b"])) <= TOL
+    x, its, conv, rn = d.ksp_solve(g["b"], np.zeros(n), ksp_type="richardson", rtol=1e-6, max_it=2000)
+    assert conv and abs(its - g["its"]) <= 1
+    assert np.linalg.norm(g["b"] - F @ x) <= 1e-6 * np.linalg.norm(g["b"])
+    d.close()
