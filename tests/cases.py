@@ -109,17 +109,3 @@ def build_inv(name):
     A, kw = PFLAREINV_CASES[name]()
     return A, hiergen.build_pflareinv(A, **kw)
 
-
-def ilu_factor_case(which):
-    """BASELINE.json configs[4] (tests/ilu_factors.c): the L or U factor of the reference's data fixture mat_stream_2364 with its
-    matrix-free Newton-basis polynomial inverse, read from tests/golden/ilu_mat_stream_2364.npz (made by tests/golden/make_ilu_golden.py).
-    Returns (F, H, golden) with golden = dict(b, apply, its)."""
-    import os
-    import scipy.sparse as sp
-    from hiergen.setup import AirOptions, Hierarchy, Inverse
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ilu_mat_stream_2364.npz"))
-    n = z["b"].size
-    F = sp.csr_matrix((z[which + "_data"], z[which + "_indices"], z[which + "_indptr"]), shape=(n, n))
-    inv = Inverse(kind="poly", inverse_type=poly.NEWTON, coeffs=z[which + "_coeffs"], diag_scale=False)
-    H = Hierarchy(A=F, levels=[], coarse_matrix=F, inv_coarse=inv, options=AirOptions())
-    return F, H, dict(b=z["b"], apply=z[which + "_apply"], its=int(z[which + "_its"]))

@@ -296,19 +296,22 @@ def test_medium_size_parity_and_linearity(built_libs):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["L", "U"])
-def test_ilu_factor_pflareinv_of_the_reference_fixture(built_libs, which):
-    """BASELINE.json configs[4] (tests/ilu_factors.c): PCPFLAREINV (Newton basis, matrix-free, order 6) on the ParILU(0) factors of
-    the reference's data fixture mat_stream_2364: the apply matches the oracle / the frozen vector to 1e-12, and the Richardson solve
-    the reference test runs (rtol 1e-6, max_it 2000) converges on the device in the same number of iterations."""
-    F, H, g = cases.ilu_factor_case(which)
-    n = F.shape[0]
+def test_ilu_factor_richardson_on_device(built_libs, which):
+    """BASELINE.json configs[4] (tests/ilu_factors.c:175-196): the Richardson solve (rtol 1e-6, unpreconditioned norm) the reference
+    test runs with PCPFLAREINV (Newton basis, matrix-free, order 6) on the ParILU(0) factors of its fixture mat_stream_2364, here
+    entirely on the device (pflare_b200_ksp_solve): converges, same iteration count as the host loop around the oracle."""
+    import scipy.sparse as sp
+    z = np.load(os.path.join(GOLD, "ilu_mat_stream.npz"))
+    n = z["b"].size
+    T = sp.csr_matrix((z[which + "_data"], z[which + "_indices"], z[which + "_indptr"]), shape=(n, n))
+    H = hiergen.build_pflareinv(T, poly.NEWTON, 6, 1, True)
+    H.inv_coarse.coeffs = z[which + "_roots"]
+    O = _oracle(H)
+    _, its_cpu, conv_cpu = richardson(T, z["b"], np.zeros(n), lambda v: O.inv_apply(1, oracle.INV_AFF, v), rtol=1e-6, max_it=2000)
     d = pflare_b200.DeviceAIR(1)
-    d.ksp_set_operator(F)
+    d.ksp_set_operator(T)
     hiergen.feed(H, d)
-    y = d.inv_apply(1, pflare_b200.INV_AFF, g["b"])
-    assert cases.rel_l2(y, g["apply"]) <= TOL
-    assert cases.rel_l2(y, _oracle(H).inv_apply(1, oracle.INV_AFF, g["b"])) <= TOL
-    x, its, conv, rn = d.ksp_solve(g["b"], np.zeros(n), ksp_type="richardson", rtol=1e-6, max_it=2000)
-    assert conv and abs(its - g["its"]) <= 1
-    assert np.linalg.norm(g["b"] - F @ x) <= 1e-6 * np.linalg.norm(g["b"])
+    x, its, conv, rn = d.ksp_solve(z["b"], np.zeros(n), ksp_type="richardson", rtol=1e-6, max_it=2000)
+    assert conv and conv_cpu and abs(its - its_cpu) <= 1 and its <= 5
+    assert np.linalg.norm(z["b"] - T @ x) <= 1e-6 * np.linalg.norm(z["b"])
     d.close()

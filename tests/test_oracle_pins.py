@@ -157,18 +157,3 @@ def test_cf_splitting_is_a_disjoint_cover(built_libs):
         assert both.size == lv.n and np.array_equal(np.sort(both), np.arange(lv.n))
         assert np.all(np.diff(lv.is_fine) > 0) and np.all(np.diff(lv.is_coarse) > 0)
 
-
-@pytest.mark.parametrize("which", ["L", "U"])
-def test_ilu_factor_solves_of_the_reference_fixture(built_libs, which):
-    """BASELINE.json configs[4]: tests/ilu_factors.c runs Richardson (rtol 1e-6, unpreconditioned norm, max_it 2000) with
-    PCPFLAREINV (Newton basis, matrix-free, order 6) on the ParILU(0) factors of data/mat_stream_2364 and requires every
-    solve to converge (ilu_factors.c:69-97,175-196).  The factors come from the reference's own data file
-    (tests/golden/make_ilu_golden.py); the oracle must converge, reproduce the frozen apply and the frozen iteration count."""
-    from krylov import richardson
-    F, H, g = cases.ilu_factor_case(which)
-    O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))
-    y = O.inv_apply(1, oracle.INV_AFF, g["b"])
-    assert cases.rel_l2(y, g["apply"]) <= 1e-13
-    x, its, conv = richardson(F, g["b"], np.zeros(F.shape[0]), lambda v: O.inv_apply(1, oracle.INV_AFF, v), rtol=1e-6, max_it=2000)
-    assert conv and its == g["its"] <= 2000
-    assert np.linalg.norm(g["b"] - F @ x) <= 1e-6 * np.linalg.norm(g["b"])
