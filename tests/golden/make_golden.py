@@ -11,6 +11,11 @@
                           roots of PCPFLAREINV (order 6, matrix-free, ilu_factors.c:122-126), rhs and
                           the oracle's PCApply output.
 
+  * bus1138_newton.npz  : the reference's fixture tests/data/1138_bus with the high-order Newton-basis GMRES polynomials of
+                          tests/Makefile:199-205 (PCPFLAREINV newton, matrix-free, order 60 and 120 "with added roots",
+                          src/Gmres_Poly_Newton.F90:630-700): matrix, roots, a seeded initial guess, the oracle's apply.
+                          (`python tests/golden/make_golden.py bus1138` regenerates only this file.)
+
 The reference holds no vector-level golden outputs for PCApply, so the stored
 outputs are the ORACLE's (pinned by the iteration-count bounds of tests/test_oracle_pins.py); they
 freeze the oracle against drift and give the GPU tests fixed inputs independent of hiergen's RNG.
@@ -30,7 +35,26 @@ import oracle  # noqa: E402
 from hiergen import io as hio, poly  # noqa: E402
 
 
+def make_bus1138():
+    mats, _ = hiergen.read_petsc_binary("/root/reference/tests/data/1138_bus")
+    A = mats[0].tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    out = {"indptr": A.indptr.astype(np.int32), "indices": A.indices.astype(np.int32), "data": A.data, "x0": np.random.default_rng(0).random(n),
+           "v": cases.rhs(n)}
+    for order in (60, 120):
+        H = hiergen.build_pflareinv(A, poly.NEWTON, order, 1, True)
+        O = hiergen.feed(H, oracle.OracleAIR(1))
+        out["roots_%d" % order] = np.asarray(H.inv_coarse.coeffs)
+        out["y_oracle_%d" % order] = O.inv_apply(1, oracle.INV_AFF, out["v"])
+        print("1138_bus order", order, "roots", out["roots_%d" % order].shape)
+    np.savez_compressed(os.path.join(HERE, "bus1138_newton.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "bus1138":
+        return make_bus1138()
+    make_bus1138()
     for name in cases.GOLDEN:
         A, H = cases.build(name)
         O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))

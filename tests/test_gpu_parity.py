@@ -315,3 +315,26 @@ def test_ilu_factor_richardson_on_device(built_libs, which):
     assert conv and conv_cpu and abs(its - its_cpu) <= 1 and its <= 5
     assert np.linalg.norm(z["b"] - T @ x) <= 1e-6 * np.linalg.norm(z["b"])
     d.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order,bound", [(60, 6), (120, 5)])
+def test_1138_bus_high_order_newton_on_device(built_libs, order, bound):
+    """tests/Makefile:199-205 on the reference's fixture data/1138_bus: PCPFLAREINV Newton basis, matrix-free, order 60 / 120 with
+    the added roots (86 / 239 roots = as many fused SpMV launches per apply).  The device apply matches the frozen oracle vector to
+    1e-12 and the right-preconditioned GMRES of the reference's run (b = 0, random x0, rtol 1e-5) stays within its -ksp_max_it."""
+    import scipy.sparse as sp
+    z = np.load(os.path.join(GOLD, "bus1138_newton.npz"))
+    n = z["x0"].size
+    A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+    H = hiergen.build_pflareinv(A, poly.NEWTON, order, 1, True)
+    H.inv_coarse.coeffs = z["roots_%d" % order]
+    d = pflare_b200.DeviceAIR(1)
+    d.ksp_set_operator(A)
+    hiergen.feed(H, d)
+    assert cases.rel_l2(d.inv_apply(1, pflare_b200.INV_AFF, z["v"]), z["y_oracle_%d" % order]) <= TOL
+    O = _oracle(H)
+    _, its_cpu, _ = gmres(A, np.zeros(n), z["x0"], lambda v: O.inv_apply(1, oracle.INV_AFF, v), rtol=1e-5, side="right")
+    x, its, conv, rn = d.ksp_solve(np.zeros(n), z["x0"], ksp_type="gmres", side="right", rtol=1e-5)
+    assert conv and its <= bound and abs(its - its_cpu) <= 1
+    d.close()

@@ -83,6 +83,31 @@ def test_pin_ilu_factors_newton(built_libs):
         assert conv and its <= 5
 
 
+def _bus1138(order):
+    import scipy.sparse as sp
+    z = np.load(os.path.join(GOLD, "bus1138_newton.npz"))
+    n = z["x0"].size
+    A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+    H = hiergen.build_pflareinv(A, poly.NEWTON, order, 1, True)
+    H.inv_coarse.coeffs = z["roots_%d" % order]
+    return A, H, z
+
+
+@pytest.mark.parametrize("order,bound", [(60, 6), (120, 5)])
+def test_pin_1138_bus_high_order_newton(built_libs, order, bound):
+    """tests/Makefile:199-205: `ex6 -b_in_f 0 -f data/1138_bus -pc_type pflareinv -pc_pflareinv_type newton -pc_pflareinv_poly_order
+    60|120 -pc_pflareinv_matrix_free -ksp_norm_type unpreconditioned -ksp_max_it 6|5` on the reference's own data fixture (GMRES,
+    b = 0, random initial guess, rtol 1e-5; the unpreconditioned norm makes PETSc's GMRES right-preconditioned).  The Newton
+    polynomial with the added roots (86 / 239 stored roots, src/Gmres_Poly_Newton.F90:630-700) is the longest product chain the
+    apply path runs: the oracle must stay within the reference's iteration bound and reproduce the frozen apply."""
+    A, H, z = _bus1138(order)
+    O = _oracle(H)
+    assert cases.rel_l2(O.inv_apply(1, oracle.INV_AFF, z["v"]), z["y_oracle_%d" % order]) < 1e-13
+    n = A.shape[0]
+    _, its, conv = gmres(A, np.zeros(n), z["x0"], lambda v: O.inv_apply(1, oracle.INV_AFF, v), rtol=1e-5, side="right")
+    assert conv and its <= bound
+
+
 # ------------------------------------------------------------------ oracle vs independent evaluation
 @pytest.mark.parametrize("name", sorted(cases.CASES))
 def test_oracle_matches_textbook_cycle(built_libs, name):
