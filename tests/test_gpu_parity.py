@@ -321,8 +321,8 @@ def test_ilu_factor_richardson_on_device(built_libs, which):
 @pytest.mark.parametrize("order,bound", [(60, 6), (120, 5)])
 def test_1138_bus_high_order_newton_on_device(built_libs, order, bound):
     """tests/Makefile:199-205 on the reference's fixture data/1138_bus: PCPFLAREINV Newton basis, matrix-free, order 60 / 120 with
-    the added roots (86 / 239 roots = as many fused SpMV launches per apply).  The device apply matches the frozen oracle vector to
-    1e-12 and the right-preconditioned GMRES of the reference's run (b = 0, random x0, rtol 1e-5) stays within its -ksp_max_it."""
+    the added roots (86 / 239 roots = as many fused SpMV launches per apply).  The device apply matches the frozen oracle vector (1e-12
+    at order 60; at order 120 within the chain's measured rounding sensitivity, see below) and the right-preconditioned GMRES of the reference's run (b = 0, random x0, rtol 1e-5) stays within its -ksp_max_it."""
     import scipy.sparse as sp
     z = np.load(os.path.join(GOLD, "bus1138_newton.npz"))
     n = z["x0"].size
@@ -332,8 +332,20 @@ def test_1138_bus_high_order_newton_on_device(built_libs, order, bound):
     d = pflare_b200.DeviceAIR(1)
     d.ksp_set_operator(A)
     hiergen.feed(H, d)
-    assert cases.rel_l2(d.inv_apply(1, pflare_b200.INV_AFF, z["v"]), z["y_oracle_%d" % order]) <= TOL
     O = _oracle(H)
+    # Order 60 meets the 1e-12 bar.  The order-120 chain (239 products) amplifies rounding: the ORACLE evaluated on the symmetrically
+    # permuted matrix (same polynomial, same arithmetic, only the order of the row sums changes) already differs from itself by
+    # ~4e-11, so the bar for that case is 20 x this measured rounding sensitivity (the device sums rows in tile order).
+    p = np.random.default_rng(5).permutation(n)
+    Ap = A[p][:, p].tocsr()
+    Ap.sort_indices()
+    Hp = hiergen.build_pflareinv(Ap, poly.NEWTON, order, 1, True)
+    Hp.inv_coarse.coeffs = z["roots_%d" % order]
+    yp = np.empty(n)
+    yp[p] = _oracle(Hp).inv_apply(1, oracle.INV_AFF, z["v"][p])
+    noise = cases.rel_l2(yp, z["y_oracle_%d" % order])
+    assert noise <= (TOL if order == 60 else 1e-9)
+    assert cases.rel_l2(d.inv_apply(1, pflare_b200.INV_AFF, z["v"]), z["y_oracle_%d" % order]) <= max(TOL, 20 * noise)
     _, its_cpu, _ = gmres(A, np.zeros(n), z["x0"], lambda v: O.inv_apply(1, oracle.INV_AFF, v), rtol=1e-5, side="right")
     x, its, conv, rn = d.ksp_solve(np.zeros(n), z["x0"], ksp_type="gmres", side="right", rtol=1e-5)
     assert conv and its <= bound and abs(its - its_cpu) <= 1
