@@ -15,6 +15,18 @@ def _adv2(n):
     return hiergen.adv_diff_fd(n, n)
 
 
+def _mat_stream(part="A"):
+    """The reference's own data fixture tests/data/mat_stream_2364 (unstructured streaming problem, 2364 rows, 15948 nonzeros) and
+    its rhs, as converted by tests/golden/make_golden.py (the GPU box has no /root/reference)."""
+    import os
+    import scipy.sparse as sp
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mat_stream_2364_system.npz"))
+    if part == "b":
+        return z["b"]
+    n = z["b"].size
+    return sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+
+
 CASES = {
     # tests/Makefile:537-540 (adv_1d, Newton matrix-free coarse solver, power-basis smoother)
     "adv1d_makefile": lambda: (hiergen.adv_1d(1000), O(coarsest_inverse_type=poly.NEWTON, coarsest_poly_order=10,
@@ -66,8 +78,15 @@ CASES = {
     "fd2d_full_mf": lambda: (hiergen.adv_diff_fd(40, 40, alpha=0.5), O(full_smoothing_up_and_down=True, matrix_free_polys=True)),
     "fd2d_full_mf_newton": lambda: (_adv2(40), O(full_smoothing_up_and_down=True, matrix_free_polys=True, inverse_type=poly.NEWTON)),
     "fd2d_full_jacobi": lambda: (hiergen.adv_diff_fd(32, 32, alpha=1.0), O(full_smoothing_up_and_down=True, inverse_type=poly.JACOBI)),
+    # the reference's runs on its data fixture mat_stream_2364 (tests/Makefile:89-95,113,208; all with -ksp_max_it 5)
+    "ms2364_default": lambda: (_mat_stream(), O()),
+    "ms2364_power_fcf": lambda: (_mat_stream(), O(a_drop=1e-3, inverse_type=poly.POWER, smooth_order=(1, -1, 1))),
+    "ms2364_power_mf": lambda: (_mat_stream(), O(a_drop=1e-3, inverse_type=poly.POWER, matrix_free_polys=True)),
+    "ms2364_power_lair": lambda: (_mat_stream(), O(a_drop=1e-3, inverse_type=poly.POWER, z_type="lair")),
+    "ms2364_newton_mf": lambda: (_mat_stream(), O(a_drop=1e-3, inverse_type=poly.NEWTON, matrix_free_polys=True)),
 }
 
+MAT_STREAM_CASES = ["ms2364_default", "ms2364_power_fcf", "ms2364_power_mf", "ms2364_power_lair", "ms2364_newton_mf"]
 FULL_CASES = ["fd2d_full", "fd2d_full_mf", "fd2d_full_mf_newton", "fd2d_full_jacobi"]
 
 # cases small enough for the CPU-only suite and the golden fixtures

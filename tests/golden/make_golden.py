@@ -11,6 +11,9 @@
                           roots of PCPFLAREINV (order 6, matrix-free, ilu_factors.c:122-126), rhs and
                           the oracle's PCApply output.
 
+  * mat_stream_2364_system.npz : the reference's fixture tests/data/mat_stream_2364 (AIJ Mat + rhs Vec, PETSc binary) converted to
+                          npz: the matrix and rhs of the `ex12f` / `ex6 -f data/mat_stream_2364 ... -ksp_max_it 5` runs of
+                          tests/Makefile:89-99,113,208 (cases `ms2364_*` in tests/cases.py).  (`make_golden.py mat_stream`)
   * bus1138_newton.npz  : the reference's fixture tests/data/1138_bus with the high-order Newton-basis GMRES polynomials of
                           tests/Makefile:199-205 (PCPFLAREINV newton, matrix-free, order 60 and 120 "with added roots",
                           src/Gmres_Poly_Newton.F90:630-700): matrix, roots, a seeded initial guess, the oracle's apply.
@@ -51,10 +54,22 @@ def make_bus1138():
     np.savez_compressed(os.path.join(HERE, "bus1138_newton.npz"), **out)
 
 
+def make_mat_stream():
+    mats, vecs = hiergen.read_petsc_binary("/root/reference/tests/data/mat_stream_2364")
+    A = mats[0].tocsr()
+    A.sort_indices()
+    np.savez_compressed(os.path.join(HERE, "mat_stream_2364_system.npz"), indptr=A.indptr.astype(np.int32), indices=A.indices.astype(np.int32),
+                        data=A.data, b=np.asarray(vecs[0], dtype=np.float64))
+    print("mat_stream_2364_system", A.shape[0], A.nnz)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "bus1138":
         return make_bus1138()
+    if len(sys.argv) > 1 and sys.argv[1] == "mat_stream":
+        return make_mat_stream()
     make_bus1138()
+    make_mat_stream()
     for name in cases.GOLDEN:
         A, H = cases.build(name)
         O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))

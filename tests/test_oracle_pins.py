@@ -83,6 +83,18 @@ def test_pin_ilu_factors_newton(built_libs):
         assert conv and its <= 5
 
 
+@pytest.mark.parametrize("name", cases.MAT_STREAM_CASES)
+def test_pin_mat_stream_2364(built_libs, name):
+    """tests/Makefile:89-95,113,208: `ex12f -f data/mat_stream_2364 [...] -ksp_max_it 5` on the reference's own data fixture
+    (matrix AND rhs from the file, zero initial guess, left-preconditioned GMRES, rtol 1e-5; the run fails unless it converges within
+    5 iterations): default PCAIR, power basis + a_drop 1e-3 with fcf smoothing / matrix-free smoothing / lAIR Z, Newton matrix-free."""
+    A, H = cases.build(name)
+    b = cases._mat_stream("b")
+    O = _oracle(H)
+    _, its, conv = gmres(A, b, np.zeros(A.shape[0]), O.apply, rtol=1e-5, side="left")
+    assert conv and its <= 5, (name, its)
+
+
 def _bus1138(order):
     import scipy.sparse as sp
     z = np.load(os.path.join(GOLD, "bus1138_newton.npz"))
