@@ -83,6 +83,8 @@ class OracleAIR:
         """Options that change the apply (mirrors pflare_b200_set_option); unknown keys are execution-only and ignored."""
         if key == "full_smoothing_up_and_down":
             self.L.oracle_set_full_smoothing(self.h, int(bool(value)))
+        elif key == "mg_coarse_ksp_max_it":
+            self.L.oracle_set_coarse_its(self.h, int(value))
 
     def finalize(self):
         pass

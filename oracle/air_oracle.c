@@ -84,7 +84,7 @@ typedef struct {
   double *r, *z;         /* PCMG residual / Richardson work vectors (full smoothing only) */
 } level_t;
 
-typedef struct { int no_levels; int full_smoothing; level_t L[MAXLEV]; } hier_t;
+typedef struct { int no_levels; int full_smoothing; int coarse_its; level_t L[MAXLEV]; } hier_t;
 
 /* ---------------------------------------------------------------- PETSc primitives */
 static void MatMult(const csr_t *A, const double *x, double *y) {
@@ -275,14 +275,31 @@ static void mg_fc_point_richardson(level_t *L, double *b, double *x) {
 }
 
 /* ---------------------------------------------------------------- the cycle */
+/* Coarse solve of both cycles.  Default: KSPPREONLY around the PCSHELL mg_coarse_shell_apply (src/FC_Smooth.F90:29-49,
+ * src/AIR_MG_Setup.F90:1094-1102), i.e. x_L = inv_A_ff(L) b_L.  With -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it N the
+ * same KSP (KSP_NORM_NONE, zero initial guess, scale 1) runs exactly N Richardson sweeps:
+ *   x = 0 ; x += M b ; then N - 1 times  r = b - A_L x ; x += M r            (tests/Makefile:132-136 uses N = 5) */
+static void coarse_solve(hier_t *H) {
+  level_t *Lc = &H->L[H->no_levels];
+  const int n = Lc->n;
+  VecSet(n, Lc->x, 0.0);
+  inv_mult(&Lc->inv_ff, &Lc->M[W_COARSE], Lc->b, Lc->x);                                /* FC_Smooth.F90:47 */
+  for (int it = 1; it < H->coarse_its; ++it) {
+    ensure(&Lc->r, n); ensure(&Lc->z, n);
+    MatMult(&Lc->M[W_COARSE], Lc->x, Lc->r);
+    VecAYPX(n, Lc->r, -1.0, Lc->b);
+    inv_mult(&Lc->inv_ff, &Lc->M[W_COARSE], Lc->r, Lc->z);
+    VecAXPY(n, Lc->x, 1.0, Lc->z);
+  }
+}
+
 /* PETSc PCMG in PC_MG_KASKADE mode as configured by src/AIR_MG_Setup.F90:967-1156 */
 static void pcmg_kaskade(hier_t *H, const double *b_in, double *x_out) {
   const int NL = H->no_levels;
   level_t *L = H->L;
   VecCopy(L[1].n, b_in, L[1].b);
   for (int l = 1; l <= NL - 1; ++l) MatMult(&L[l].M[W_R], L[l].b, L[l + 1].b);          /* MatRestrict */
-  VecSet(L[NL].n, L[NL].x, 0.0);
-  inv_mult(&L[NL].inv_ff, &L[NL].M[W_COARSE], L[NL].b, L[NL].x);                        /* FC_Smooth.F90:47 */
+  coarse_solve(H);
   for (int l = NL - 1; l >= 1; --l) {
     MatMult(&L[l].M[W_P], L[l + 1].x, L[l].x);                                          /* MatInterpolate */
     mg_fc_point_richardson(&L[l], L[l].b, L[l].x);
@@ -326,8 +343,7 @@ static void pcmg_multiplicative(hier_t *H, const double *b_in, double *x_out) {
     VecAYPX(n, L[l].r, -1.0, L[l].b);
     MatMult(&L[l].M[W_R], L[l].r, L[l + 1].b);
   }
-  VecSet(L[NL].n, L[NL].x, 0.0);
-  inv_mult(&L[NL].inv_ff, &L[NL].M[W_COARSE], L[NL].b, L[NL].x);
+  coarse_solve(H);
   for (int l = NL - 1; l >= 1; --l) {
     const int n = L[l].n;
     MatMultAddInPlace(&L[l].M[W_P], L[l + 1].x, L[l].x);
@@ -422,6 +438,8 @@ int oracle_pcapply(void *h, const double *b, double *x) {
 
 /* -pc_air_full_smoothing_up_and_down: inv_A_ff(l) then inverts coarse_matrix(l) (set as W_COARSE on every level) */
 void oracle_set_full_smoothing(void *h, int flag) { ((hier_t *)h)->full_smoothing = flag; }
+/* -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it n */
+void oracle_set_coarse_its(void *h, int n) { ((hier_t *)h)->coarse_its = n < 1 ? 1 : n; }
 
 /* PCApply_PFLAREINV_c: y = mat_inverse * x (src/PCPFLAREINV.c:618-626); also used by tests to
  * exercise any level's inverse on its own.  which = W_INV_AFF (matrix W_AFF, or W_COARSE on

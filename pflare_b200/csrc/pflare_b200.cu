@@ -218,6 +218,7 @@ struct Ctx {
   int graph_kernels = 0;
   // options
   int use_graph = 1, fuse = 1;
+  int coarse_its = 1;   // -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it N: Richardson iterations of the coarse solve (KSP_NORM_NONE: exactly N)
   int fuse_epi = 1;      // compile-time specialised epilogue classes (0: every op runs the generic epilogue)
   int fuse_perm = 0;     // (measured slower: natural-order accesses interleave F and C points -> half-used sectors) natural <-> nested permutation of b / x fused into the level-1 ops (serial Kaskade contexts)
   bool io_fused = false; // decided at finalize_setup
@@ -1426,6 +1427,16 @@ int build_program(Ctx *c) {
     B.level = NL;
     int rc = B.emit_inv(Lv.inv_ff, Lv.Coarse, Lv.coarse_diag, Lv.n, c->bb + Lv.boff, c->xb + Lv.xoff, 1);
     if (rc) return rc;
+    // -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it N (src/AIR_MG_Setup.F90:1094-1102: KSP_NORM_NONE, zero initial guess):
+    // N - 1 more sweeps x_L += inv_A_ff(L) (b_L - A_L x_L)
+    for (int it = 1; it < c->coarse_its; ++it) {
+      if (!Lv.Coarse.valid()) return fail(4, "mg_coarse_ksp_max_it > 1 needs coarse_matrix(no_levels) (set_csr(..., PFLARE_B200_COARSE))");
+      SpmvOp s = B.base(Lv.Coarse, c->xb + Lv.xoff);
+      s.aux = c->bb + Lv.boff; s.alpha = 1.0; s.beta = -1.0;
+      s.out = c->scr[1]; s.out_mode = 1;
+      B.push_spmv(s, Lv.Coarse, 4, 1, 1);
+      if ((rc = B.emit_inv(Lv.inv_ff, Lv.Coarse, Lv.coarse_diag, Lv.n, c->scr[1], c->xb + Lv.xoff, 2))) return rc;
+    }
   }
   // up: x_l = P x_{l+1}; one mg_FC_point_richardson
   for (int l = LB - 1; !c->full_smooth && l >= 1; --l) {
@@ -1592,6 +1603,7 @@ int build_child(Ctx *c, const std::vector<std::vector<char>> &blobs) {
   ch->rank = 0; ch->nranks = 1; ch->device = c->device; ch->no_levels = NL - LA + 1;
   ch->L.resize((size_t)ch->no_levels + 1);
   ch->num_sms = c->num_sms; ch->stream = c->stream; ch->own_stream = false;
+  ch->coarse_its = c->coarse_its;
   ch->use_graph = 0; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->full_smooth = c->full_smooth; ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   ch->kernel = c->kernel; ch->wt_format = c->wt_format; ch->fmt_split = c->fmt_split; ch->engine = c->engine; ch->sv_pf = c->sv_pf; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
   std::vector<Reader> rd;
@@ -3010,6 +3022,12 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
     c->engine = (int)value;
   }
   else if (k == "sv_pf") c->sv_pf = value != 0;
+  else if (k == "mg_coarse_ksp_max_it") {
+    if (value < 1 || value > 1000) return fail(2, "mg_coarse_ksp_max_it must be between 1 and 1000");
+    c->coarse_its = (int)value;
+    c->dense_built = false;                       // the collapsed tail contains the coarse solve
+    if (c->child) c->child->dense_built = false;
+  }
   else if (k == "wt_stages") {
     if (value != 2) return fail(2, "wt_stages: only the 2-deep ring is compiled in (3 and 4 deep measured slower: 2.79 / 2.91 / 3.96 ms)");
     c->wt_stages = (int)value;
@@ -3040,7 +3058,7 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
   else return fail(2, "unknown option '%s'", k.c_str());
   if (c->child) {
     Ctx *ch = c->child.get();
-    ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->sv_pf = c->sv_pf; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
+    ch->coarse_its = c->coarse_its; ch->fuse = c->fuse; ch->fuse_epi = c->fuse_epi; ch->engine = c->engine; ch->sv_pf = c->sv_pf; ch->wt_stages = c->wt_stages; ch->ctas_per_sm = c->ctas_per_sm; ch->max_ctas = c->max_ctas;
     ch->dense_rows = c->dense_rows; ch->pdl = c->pdl;
   }
   return 0;

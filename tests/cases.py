@@ -87,6 +87,18 @@ CASES = {
 }
 
 MAT_STREAM_CASES = ["ms2364_default", "ms2364_power_fcf", "ms2364_power_mf", "ms2364_power_lair", "ms2364_newton_mf"]
+
+# Not part of CASES (the generic per-case tests compare against an explicitly evaluated polynomial, which these order-18 / order-60
+# coarse polynomials are too ill-conditioned for): used by the exact-solver pins and the coarse-iteration tests only.
+EXACT_CASES = {
+    # AIRG as an exact solver on the same fixture (tests/Makefile:132-145): no dropping, Jacobi smoothing, truncated hierarchy, high-order
+    # matrix-free coarse polynomial; the first one needs -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it 5 (option mg_coarse_ksp_max_it)
+    "ms2364_exact_arnoldi18": lambda: (_mat_stream(), O(strong_threshold=0.0, a_drop=0.0, r_drop=0.0, inverse_type=poly.JACOBI, max_levels=30,
+                                                         coarsest_poly_order=18, coarsest_matrix_free_polys=True, coarsest_inverse_type=poly.ARNOLDI)),
+    "ms2364_exact_newton60": lambda: (_mat_stream(), O(strong_threshold=0.0, a_drop=0.0, r_drop=0.0, inverse_type=poly.JACOBI, max_levels=10,
+                                                        coarsest_poly_order=60, coarsest_matrix_free_polys=True, coarsest_inverse_type=poly.NEWTON)),
+}
+
 FULL_CASES = ["fd2d_full", "fd2d_full_mf", "fd2d_full_mf_newton", "fd2d_full_jacobi"]
 
 # cases small enough for the CPU-only suite and the golden fixtures
@@ -95,7 +107,7 @@ GOLDEN = ["adv1d_makefile", "fd2d_25", "fd3d_10_lump", "fd2d_mf_newton", "fd2d_f
 
 @functools.lru_cache(maxsize=None)
 def build(name):
-    A, opts = CASES[name]()
+    A, opts = (CASES[name] if name in CASES else EXACT_CASES[name])()
     H = hiergen.build_hierarchy(A, opts)
     return A, H
 

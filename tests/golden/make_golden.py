@@ -14,6 +14,8 @@
   * mat_stream_2364_system.npz : the reference's fixture tests/data/mat_stream_2364 (AIJ Mat + rhs Vec, PETSc binary) converted to
                           npz: the matrix and rhs of the `ex12f` / `ex6 -f data/mat_stream_2364 ... -ksp_max_it 5` runs of
                           tests/Makefile:89-99,113,208 (cases `ms2364_*` in tests/cases.py).  (`make_golden.py mat_stream`)
+  * e05r0100_system.npz : the reference's fixture tests/data/e05r0100_petsc converted to npz (tests/Makefile:157: `ex6 -f
+                          data/e05r0100_petsc -b_in_f 0 -pc_air_a_drop 1e-3 -pc_air_inverse_type power -ksp_max_it 26`).
   * bus1138_newton.npz  : the reference's fixture tests/data/1138_bus with the high-order Newton-basis GMRES polynomials of
                           tests/Makefile:199-205 (PCPFLAREINV newton, matrix-free, order 60 and 120 "with added roots",
                           src/Gmres_Poly_Newton.F90:630-700): matrix, roots, a seeded initial guess, the oracle's apply.
@@ -54,6 +56,14 @@ def make_bus1138():
     np.savez_compressed(os.path.join(HERE, "bus1138_newton.npz"), **out)
 
 
+def make_e05r():
+    mats, _ = hiergen.read_petsc_binary("/root/reference/tests/data/e05r0100_petsc")
+    A = mats[0].tocsr()
+    A.sort_indices()
+    np.savez_compressed(os.path.join(HERE, "e05r0100_system.npz"), indptr=A.indptr.astype(np.int32), indices=A.indices.astype(np.int32), data=A.data)
+    print("e05r0100_system", A.shape[0], A.nnz)
+
+
 def make_mat_stream():
     mats, vecs = hiergen.read_petsc_binary("/root/reference/tests/data/mat_stream_2364")
     A = mats[0].tocsr()
@@ -68,8 +78,11 @@ def main():
         return make_bus1138()
     if len(sys.argv) > 1 and sys.argv[1] == "mat_stream":
         return make_mat_stream()
+    if len(sys.argv) > 1 and sys.argv[1] == "e05r":
+        return make_e05r()
     make_bus1138()
     make_mat_stream()
+    make_e05r()
     for name in cases.GOLDEN:
         A, H = cases.build(name)
         O = hiergen.feed(H, oracle.OracleAIR(H.no_levels))

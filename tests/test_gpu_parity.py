@@ -350,3 +350,26 @@ def test_1138_bus_high_order_newton_on_device(built_libs, order, bound):
     x, its, conv, rn = d.ksp_solve(np.zeros(n), z["x0"], ksp_type="gmres", side="right", rtol=1e-5)
     assert conv and its <= bound and abs(its - its_cpu) <= 1
     d.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [dict(dense_rows=0), dict()], ids=["sparse_all_levels", "dense_tail_default"])
+def test_coarse_richardson_iterations(built_libs, mode):
+    """-mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it 5 (option mg_coarse_ksp_max_it; tests/Makefile:132-136 on the reference's
+    fixture mat_stream_2364): parity with the oracle, set before and after finalize_setup, and the outer Richardson of the reference's
+    run converges in one iteration only with the five coarse sweeps."""
+    A, H = cases.build("ms2364_exact_arnoldi18")
+    b = cases._mat_stream("b")
+    n = A.shape[0]
+    O5 = _oracle(H)
+    O5.set_option("mg_coarse_ksp_max_it", 5)
+    x5, x1 = O5.apply(b), _oracle(H).apply(b)
+    d = _device(H, mg_coarse_ksp_max_it=5, **mode)
+    x = d.apply(b)
+    assert cases.rel_l2(x, x5) <= TOL
+    assert np.linalg.norm(b - A @ x) <= 1e-5 * np.linalg.norm(b) < np.linalg.norm(b - A @ x1)
+    d.set_option("mg_coarse_ksp_max_it", 1)          # rebuilds the program (and the collapsed tail) on the live handle
+    assert cases.rel_l2(d.apply(b), x1) <= TOL
+    d.set_option("mg_coarse_ksp_max_it", 5)
+    assert cases.rel_l2(d.apply(b), x5) <= TOL
+    d.close()

@@ -95,6 +95,40 @@ def test_pin_mat_stream_2364(built_libs, name):
     assert conv and its <= 5, (name, its)
 
 
+@pytest.mark.parametrize("name,coarse_its", [("ms2364_exact_arnoldi18", 5), ("ms2364_exact_newton60", 1)])
+def test_pin_mat_stream_exact_solver(built_libs, name, coarse_its):
+    """tests/Makefile:132-145: AIRG as an exact solver on data/mat_stream_2364 -- outer `-ksp_type richardson -ksp_norm_type
+    unpreconditioned -ksp_max_it 1` must converge (rtol 1e-5) in ONE iteration.  The Arnoldi-18 variant runs
+    `-mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it 5`: with a single coarse sweep the residual stalls at 1.3e-5 (> rtol), with
+    the five Richardson sweeps of the reference's run it drops to 1e-15 -- this pins the coarse-iteration semantics."""
+    A, H = cases.build(name)
+    b = cases._mat_stream("b")
+    n = A.shape[0]
+    O = _oracle(H)
+    O.set_option("mg_coarse_ksp_max_it", coarse_its)
+    x, its, conv = richardson(A, b, np.zeros(n), O.apply, rtol=1e-5, max_it=1)
+    assert conv and its == 1
+    if coarse_its > 1:
+        O1 = _oracle(H)
+        _, _, conv1 = richardson(A, b, np.zeros(n), O1.apply, rtol=1e-5, max_it=1)
+        assert not conv1
+        assert np.linalg.norm(b - A @ x) <= 1e-12 * np.linalg.norm(b)
+
+
+def test_pin_e05r0100_power(built_libs):
+    """tests/Makefile:157: `ex6 -f data/e05r0100_petsc -b_in_f 0 -pc_air_a_drop 1e-3 -pc_air_inverse_type power -ksp_max_it 26` on the
+    reference's data fixture (b = 0, random initial guess, GMRES rtol 1e-5): a hard non-symmetric problem where AIRG needs ~23 iterations."""
+    import scipy.sparse as sp
+    from hiergen import AirOptions
+    z = np.load(os.path.join(GOLD, "e05r0100_system.npz"))
+    n = z["indptr"].size - 1
+    A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+    H = hiergen.build_hierarchy(A, AirOptions(a_drop=1e-3, inverse_type=poly.POWER))
+    O = _oracle(H)
+    _, its, conv = gmres(A, np.zeros(n), np.random.default_rng(0).random(n), O.apply, rtol=1e-5, side="left")
+    assert conv and its <= 26, its
+
+
 def _bus1138(order):
     import scipy.sparse as sp
     z = np.load(os.path.join(GOLD, "bus1138_newton.npz"))
