@@ -206,6 +206,9 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
  *   "full_smoothing_up_and_down" (before finalize_setup)  -pc_air_full_smoothing_up_and_down: PCMG multiplicative V(1,1), one
  *                  Richardson sweep with inv_A_ff(level) on ALL unknowns down and up, residual restriction R (b - A x)
  *                  (src/AIR_MG_Setup.F90:978-1074); the hook hands over coarse_matrix(level) + inv_A_ff(level) instead of A_ff / A_fc.
+ *   "mg_coarse_ksp_max_it" N (default 1)  -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it N: the coarse solve runs N Richardson
+ *                  sweeps x_L += inv_A_ff(L) (b_L - A_L x_L) from a zero guess (KSP_NORM_NONE: exactly N, src/AIR_MG_Setup.F90:1094-1102;
+ *                  tests/Makefile:132-136 uses 5); needs coarse_matrix(no_levels); may be changed on a finalized handle.
  * Execution switches (results stay within the 1e-12 parity bar):
  *   "graph" (0/1) CUDA graph of the cycle; "pdl" programmatic dependent launch; "fuse" (0: one kernel per PETSc call instead of
  *   the fused epilogues); "epi_classes" (0: run-time branched epilogue instead of the compiled classes);
