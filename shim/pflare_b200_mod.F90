@@ -71,6 +71,11 @@ module pflare_b200_mod
          use iso_c_binding
          type(c_ptr) :: handle, aux
       end subroutine
+      subroutine pflare_b200_coarse_its_c(pcmg, its) bind(c, name="pflare_b200_coarse_its_c")
+         use iso_c_binding
+         integer(c_long_long) :: pcmg
+         integer(c_int) :: its
+      end subroutine
       function pflare_b200_set_option(handle, key, val) bind(c, name="pflare_b200_set_option")
          use iso_c_binding
          type(c_ptr), value :: handle
@@ -140,6 +145,12 @@ module pflare_b200_mod
       call pflare_b200_create_c(air_data%b200_handle, air_data%b200_aux, amat%v, int(no_levels, c_long_long))
       if (air_data%options%full_smoothing_up_and_down) then
          ierr_c = pflare_b200_set_option(air_data%b200_handle, "full_smoothing_up_and_down"//c_null_char, 1d0)
+      end if
+      ! -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it N: the coarse KSP of the PCMG (src/AIR_MG_Setup.F90:1094-1102) then runs
+      ! N Richardson sweeps around mg_coarse_shell_apply; KSPPREONLY (the default) is one application
+      call pflare_b200_coarse_its_c(air_data%pcmg%v, ierr_c)       ! PCMGGetCoarseSolve -> KSPGetType / KSPGetTolerances (shim C file)
+      if (ierr_c > 1) then
+         ierr_c = pflare_b200_set_option(air_data%b200_handle, "mg_coarse_ksp_max_it"//c_null_char, real(ierr_c, c_double))
       end if
       do our_level = 1, no_levels - 1
          ! the level operator fixes the row ownership of the level: level 1 = amat, else coarse_matrix(our_level)

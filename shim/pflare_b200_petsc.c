@@ -147,6 +147,22 @@ PETSC_INTERN void pflare_b200_upload_diag_c(void **handle, PetscInt our_level, i
   PetscCallVoid(VecDestroy(&d));
 }
 
+/* Richardson sweeps of the PCMG coarse solve (option "mg_coarse_ksp_max_it"): KSPPREONLY (the default of
+ * src/AIR_MG_Setup.F90:1094-1102) = 1, -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it N = N. */
+PETSC_INTERN void pflare_b200_coarse_its_c(PC *pcmg, int *its)
+{
+  KSP       coarse;
+  PetscBool is_rich;
+  PetscInt  max_it;
+  *its = 1;
+  PetscCallVoid(PCMGGetCoarseSolve(*pcmg, &coarse));
+  PetscCallVoid(PetscObjectTypeCompare((PetscObject)coarse, KSPRICHARDSON, &is_rich));
+  if (is_rich) {
+    PetscCallVoid(KSPGetTolerances(coarse, NULL, NULL, NULL, &max_it));
+    *its = (int)max_it;
+  }
+}
+
 /* Stream ordering around a device-pointer call.  The library runs on its own non-blocking stream
  * (pflare_b200_get_stream); PETSc's kernels that produced x run on the PetscDeviceContext's stream.  BEFORE the call
  * the library stream waits for PETSc's stream, AFTER it PETSc's stream waits for the library's: no host
