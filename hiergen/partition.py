@@ -58,6 +58,7 @@ class LocalHierarchy:
         self.rangesV = []     # per level: global ownership offsets (nranks + 1)
         self.rangesF = []
         self.full_smoothing = False   # -pc_air_full_smoothing_up_and_down
+        self.coarse_its = 1           # -mg_coarse_ksp_max_it
 
     def local_rows(self):
         return self.levels[0]["n"]
@@ -68,6 +69,8 @@ class LocalHierarchy:
     def feed(self, sink):
         if self.full_smoothing:
             sink.set_option("full_smoothing_up_and_down", 1)
+        if self.coarse_its > 1:
+            sink.set_option("mg_coarse_ksp_max_it", self.coarse_its)
         for l, lv in enumerate(self.levels, start=1):
             sink.set_level(l, lv["n"], lv["is_fine"], lv["is_coarse"], lv["smooth"], rstart=lv["rstart"])
             for which, op in lv["ops"].items():
@@ -94,6 +97,7 @@ def partition(H, nranks, only=None):
     full = bool(getattr(H.options, "full_smoothing_up_and_down", False))
     for lh in out:
         lh.full_smoothing = full
+        lh.coarse_its = int(getattr(H.options, "mg_coarse_ksp_max_it", 1) or 1)
     todo = range(nranks) if only is None else [only]
     rv = split_ownership(H.levels[0].n if H.levels else H.coarse_matrix.shape[0], nranks)
 

@@ -59,6 +59,8 @@ class AirOptions:
     # system Z(i,J) A_ff(J,J) = -A_cf(i,J) on the distance-d F neighbourhood J (pattern of A_cf A_ff^(d-1))
     z_type: str = "product"
     lair_distance: int = 2
+    # -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it N (apply-time only: N Richardson sweeps of the coarse solve, AIR_MG_Setup.F90:1094-1102)
+    mg_coarse_ksp_max_it: int = 1
     seed: int = 1
 
     @property

@@ -25,6 +25,9 @@ def feed(H, sink):
         # -pc_air_full_smoothing_up_and_down: the smoother is inv_A_ff(level) applied to coarse_matrix(level) on all
         # unknowns (src/AIR_MG_Setup.F90:1014-1074): the hook hands over coarse_matrix, inv_A_ff, R and P per level
         sink.set_option("full_smoothing_up_and_down", 1)
+    coarse_its = int(getattr(getattr(H, "options", None), "mg_coarse_ksp_max_it", 1) or 1)
+    if coarse_its > 1:
+        sink.set_option("mg_coarse_ksp_max_it", coarse_its)
     for l, lv in enumerate(H.levels):
         ol = l + 1
         sink.set_level(ol, lv.n, lv.is_fine, lv.is_coarse, lv.smooth_order)
