@@ -115,6 +115,45 @@ def test_pin_mat_stream_exact_solver(built_libs, name, coarse_its):
         assert np.linalg.norm(b - A @ x) <= 1e-12 * np.linalg.norm(b)
 
 
+@pytest.mark.parametrize("label,kw,bound", [("default arnoldi", dict(inverse_type=poly.ARNOLDI, poly_order=6, matrix_free=False), 21),
+                                            ("power", dict(inverse_type=poly.POWER, poly_order=6, matrix_free=False), 21),
+                                            ("newton matrix-free", dict(inverse_type=poly.NEWTON, poly_order=6, matrix_free=True), 13)])
+def test_pin_mat_stream_pflareinv(built_libs, label, kw, bound):
+    """tests/Makefile:119-127: `ex6 -f data/mat_stream_2364 -pc_type pflareinv [-pc_pflareinv_type power | newton
+    -pc_pflareinv_matrix_free] -ksp_max_it 21 | 13` (matrix and rhs from the reference's file, GMRES, rtol 1e-5): single-level
+    polynomial preconditioning; measured here 20, 20 and 12 iterations."""
+    A, b = cases._mat_stream(), cases._mat_stream("b")
+    H = hiergen.build_pflareinv(A, **kw)
+    O = _oracle(H)
+    _, its, conv = gmres(A, b, np.zeros(A.shape[0]), lambda v: O.inv_apply(1, oracle.INV_AFF, v), rtol=1e-5, side="left")
+    assert conv and its <= bound, (label, its)
+
+
+@pytest.mark.parametrize("label,kw,bound,coarse_its", [
+    ("default", dict(), 5, 1),
+    ("arnoldi + a_drop", dict(inverse_type=poly.ARNOLDI, coarsest_inverse_type=poly.ARNOLDI, a_drop=1e-3), 5, 1),
+    ("neumann", dict(inverse_type=poly.NEUMANN, a_drop=1e-3), 5, 1),
+    ("neumann matrix-free", dict(inverse_type=poly.NEUMANN, a_drop=1e-3, matrix_free_polys=True), 5, 1),
+    ("wjacobi", dict(inverse_type=poly.WJACOBI, a_drop=1e-3), 8, 1),
+    ("jacobi", dict(inverse_type=poly.JACOBI, a_drop=1e-3), 5, 1),
+    ("exact solver, 10 coarse sweeps", dict(strong_threshold=0.0, a_drop=0.0, r_drop=0.0, inverse_type=poly.JACOBI), 1, 10)])
+def test_pin_diffusion_8x8(built_libs, label, kw, bound, coarse_its):
+    """tests/Makefile:386-424: `adv_diff_fd -u 0 -v 0 -alpha 1.0 -da_grid_x 8 -da_grid_y 8 -pc_type air [...] -ksp_max_it N` (b = 0,
+    x0 = 1, GMRES rtol 1e-5; the last one `-ksp_type richardson -ksp_norm_type unpreconditioned -mg_coarse_ksp_type richardson
+    -mg_coarse_ksp_max_it 10 -ksp_max_it 1`): the polynomial / Neumann / Jacobi inverse families on a diffusion stencil."""
+    from hiergen import AirOptions
+    A = hiergen.adv_diff_fd(8, 8, alpha=1.0, u=0.0, v=0.0)
+    n = A.shape[0]
+    H = hiergen.build_hierarchy(A, AirOptions(**kw))
+    O = _oracle(H)
+    O.set_option("mg_coarse_ksp_max_it", coarse_its)
+    if coarse_its > 1:
+        _, its, conv = richardson(A, np.zeros(n), np.ones(n), O.apply, rtol=1e-5, max_it=bound)
+    else:
+        _, its, conv = gmres(A, np.zeros(n), np.ones(n), O.apply, rtol=1e-5, side="left")
+    assert conv and its <= bound, (label, its)
+
+
 def test_pin_e05r0100_power(built_libs):
     """tests/Makefile:157: `ex6 -f data/e05r0100_petsc -b_in_f 0 -pc_air_a_drop 1e-3 -pc_air_inverse_type power -ksp_max_it 26` on the
     reference's data fixture (b = 0, random initial guess, GMRES rtol 1e-5): a hard non-symmetric problem where AIRG needs ~23 iterations."""
