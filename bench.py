@@ -32,7 +32,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|INFO on the box) go to stderr
+# stdout carries exactly ONE JSON line: NCCL's own banner / debug lines go to stderr.  NCCL honours NCCL_DEBUG_FILE only above
+# the VERSION level (at NCCL_DEBUG=VERSION the "NCCL version ..." banner is written to stdout regardless), so VERSION becomes WARN:
+# same banner, no extra output, but routed to the file.
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 
