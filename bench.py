@@ -28,7 +28,17 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the host-side setup (hierarchy load / partition, warp-tile packing at upload) is
+# OpenMP code, so give each rank its share of the host cores instead -- before any OpenMP runtime is loaded.  (The oracle's thread
+# count is set explicitly, host_threads().)
+if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    try:
+        _cores = len(os.sched_getaffinity(0))
+    except Exception:
+        _cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(max(1, _cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))))
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
