@@ -14,5 +14,5 @@ and the CUDA path consume.
 """
 from .problems import adv_1d, adv_diff_fd, dg_upwind_surrogate, read_petsc_binary, parilu_factors  # noqa: F401
 from .setup import AirOptions, Hierarchy, Level, Inverse, build_hierarchy, build_pflareinv  # noqa: F401
-from .upload import feed  # noqa: F401
+from pflare_b200.upload import feed  # noqa: F401  (the upload-hook walker lives with the product's boundary: oracle and CUDA path are fed by the same code)
 from .partition import partition, split_ownership, scatter_vector, LocalHierarchy  # noqa: F401
