@@ -221,7 +221,6 @@ int pflare_b200_profile_apply(void *handle, const double *b_dev, double *x_dev, 
  *   "dense_rows" levels with <= this many rows are collapsed into one dense operator built from the same kernels at setup (0 = off);
  *   "fuse_perm" (before finalize_setup) 0 (default) / 1 / 2: entry / exit permutation fused into the level-1 ops (measured slower);
  *   "agg_rows" (multi-rank, before finalize_setup) levels with <= this many global rows are agglomerated onto rank 0 (0 = never);
- *   "sv_pf" direct engine with the next tile's column indices loaded one tile ahead (measured slower, default 0);
  *   "p2p" (multi-rank, before finalize_setup) ghost exchange: 2 (default) = fused: the consuming SpMV kernel pushes this rank's
  *                  boundary entries straight into the peers' ghost buffers (CUDA IPC peer memory, one buffer per exchange of the
  *                  cycle, ready flags per exchange, one "entered the cycle" flag per cycle), multiplies its interior tiles and

@@ -229,7 +229,7 @@ struct Ctx {
   int wt_format = 0;     // kernel 2 operator storage: 0 = by mean row length (fmt_split), 1 = chunk format, 2 = row-aligned lanes
   double fmt_split = 8.0;   // measured on the 4096^2 cycle: 3 -> 2.82 ms, 4.5 -> 2.65 ms, 8 -> 2.62 ms
   int engine = 1;        // kernel 2, row-aligned storage: 1 = direct engine (spmv_sv_kernel), 0 = TMA-ring engine (spmv_wt_kernel, A/B) // 0 = TMA-ring engine (spmv_wt_kernel), 1 = direct engine (spmv_sv_kernel), 2 = thin-warp engine (spmv_thin_kernel)
-  int sv_pf = 0;         // direct engine: 1 = column indices prefetched one tile ahead (3 CTAs per SM)
+  int sv_pf = 0;         // (retired A/B switch, always 0: see set_option)
   int wt_stages = 2;     // ring depth of the warp-tile kernel (2 or 3 tiles per warp; 2 leaves more of the SM's L1 to the gathers)
   int ctas_per_sm = 0;   // 0 = from the occupancy calculator
   int max_ctas = 0;      // > 0: cap on the persistent grid (tests: forces many tiles per CTA / warp)
@@ -1010,7 +1010,6 @@ int launch_sv_inst(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
 template <int EPI, int KP>
 int launch_wt_kp(Ctx *c, const SpmvOp &s, cudaStream_t st, bool dry) {
   const bool gh = s.xg != nullptr;
-  if (c->engine == 1 && c->sv_pf) return gh ? launch_sv_inst<EPI, KP, true, 1>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 1>(c, s, st, dry);
   if (c->engine == 1) return gh ? launch_sv_inst<EPI, KP, true, 0>(c, s, st, dry) : launch_sv_inst<EPI, KP, false, 0>(c, s, st, dry);
   return gh ? launch_wt_inst<EPI, KP, true, 2>(c, s, st, dry) : launch_wt_inst<EPI, KP, false, 2>(c, s, st, dry);
 }
@@ -3021,7 +3020,11 @@ static int set_option_ctx(Ctx *c, const std::string &k, double value) {
     if (value != 0 && value != 1) return fail(2, "engine must be 0 (TMA ring) or 1 (direct)");
     c->engine = (int)value;
   }
-  else if (k == "sv_pf") c->sv_pf = value != 0;
+  else if (k == "sv_pf") {
+    // the direct engine with the next tile's column indices loaded one tile ahead (template parameter PF of spmv_sv_kernel,
+    // 80 registers, 3 CTAs per SM) was measured slower (8.84 vs 8.55 ms on 3D 256^3) and is no longer instantiated
+    if (value != 0) return fail(2, "sv_pf=1 was measured slower than the default direct engine and is not compiled into the library");
+  }
   else if (k == "mg_coarse_ksp_max_it") {
     if (value < 1 || value > 1000) return fail(2, "mg_coarse_ksp_max_it must be between 1 and 1000");
     c->coarse_its = (int)value;
