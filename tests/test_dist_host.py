@@ -172,3 +172,26 @@ def test_group_finalize_fails_instead_of_hanging_when_one_rank_is_incomplete(bui
         cl.finalize()
     assert "rank 1" in str(e.value)
     cl.close()
+
+
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_resetup_on_a_live_handle_host_logic(built_libs, nranks):
+    """The reference's re-setup (src/PCAIR_Shell.F90:148-162, SAME_NONZERO_PATTERN): the upload hook runs again on the SAME handle
+    and finalize_setup rebuilds from the new host operators (host-only planning group: the plans, counters and programme of the
+    second setup equal those of a fresh handle fed with the same operators; the device side of the path is covered by test_gpu_parity.py::test_resetup_on_a_live_handle)."""
+    A, H = cases.build("fd2d_64")
+    H2 = hiergen.build_hierarchy(1.7 * A, cases.CASES["fd2d_64"]()[1])
+    ref = pflare_b200.ClusterAIR(H2.no_levels, nranks, device=-1)
+    ref.upload(hiergen.partition(H2, nranks))
+    want = [r.stats() for r in ref.ranks]
+    ref.close()
+    cl = pflare_b200.ClusterAIR(H.no_levels, nranks, device=-1)
+    cl.upload(hiergen.partition(H, nranks))
+    first = [r.stats() for r in cl.ranks]
+    cl.upload(hiergen.partition(H2, nranks))            # second setup on the live handles
+    again = [r.stats() for r in cl.ranks]
+    for a, w in zip(again, want):
+        for k in ("kernel_launches", "exchange_groups", "nnz_per_cycle", "algorithmic_bytes", "ghost_bytes_sent"):
+            assert a[k] == w[k], k
+    assert sum(a["nnz_per_cycle"] for a in again) != sum(f["nnz_per_cycle"] for f in first)      # the new operators really replaced the old ones
+    cl.close()

@@ -377,3 +377,24 @@ def test_coarse_richardson_iterations(built_libs, mode):
     d.set_option("mg_coarse_ksp_max_it", 5)
     assert cases.rel_l2(d.apply(b), x5) <= TOL
     d.close()
+
+
+@pytest.mark.gpu
+def test_resetup_on_a_live_handle(built_libs):
+    """The reference's re-setup (src/PCAIR_Shell.F90:148-162): the upload hook runs again on the SAME handle with new operators and
+    finalize_setup releases everything the previous setup put on the device (operators, plans, dense tail, graph) before it rebuilds --
+    old and new state are never mixed (the collapsed coarse tail in particular is rebuilt from the new values)."""
+    A, H = cases.build("fd2d_64")
+    H2 = hiergen.build_hierarchy(1.7 * A, cases.CASES["fd2d_64"]()[1])
+    b = cases.rhs(A.shape[0])
+    x1, x2 = _oracle(H).apply(b), _oracle(H2).apply(b)
+    assert cases.rel_l2(x1, x2) > 0.1
+    d = _device(H)
+    assert cases.rel_l2(d.apply(b), x1) <= TOL
+    before = d.stats()["device_bytes"]
+    hiergen.feed(H2, d)
+    assert cases.rel_l2(d.apply(b), x2) <= TOL
+    hiergen.feed(H, d)
+    assert cases.rel_l2(d.apply(b), x1) <= TOL
+    assert abs(d.stats()["device_bytes"] - before) <= 0.01 * before          # nothing of the two earlier setups is still allocated
+    d.close()
