@@ -18,6 +18,8 @@
  *                             unknowns down and up, true residual restriction R (b - A x)
  *                             (src/AIR_MG_Setup.F90:978-1074, src/AIR_Operators_Setup.F90:115-119)
  *   mg_coarse_shell_apply()   src/FC_Smooth.F90:29-49
+ *   coarse_solve()            the coarse KSP around it (src/AIR_MG_Setup.F90:1094-1102): PREONLY, or N Richardson
+ *                             sweeps with -mg_coarse_ksp_type richardson -mg_coarse_ksp_max_it N (tests/Makefile:132-136)
  *   mg_fc_point_richardson()  src/FC_Smooth.F90:421-495
  *   f_smooths()               src/FC_Smooth.F90:499-568
  *   c_smooths()               src/FC_Smooth.F90:572-640
@@ -36,7 +38,8 @@
  *
  * PARITY PINNING: the reference holds no vector-level golden outputs for PCApply
  * (SURVEY.md section 8c).  What it does hold are known-answer iteration bounds (tests/Makefile),
- * and those are what tests/test_oracle_pins.py checks this oracle against.  Vector-level
+ * and those are what tests/test_oracle_pins.py checks this oracle against -- including the runs on the
+ * reference's own data fixtures (mat_stream_2364 with its rhs, its ParILU factors, 1138_bus, e05r0100).  Vector-level
  * parity against a real PFLARE build is therefore UNPINNED ("parity unpinned").
  *
  * Rows are processed with OpenMP `parallel for`; per-row summation order is unchanged.
