@@ -154,6 +154,18 @@ def test_pin_diffusion_8x8(built_libs, label, kw, bound, coarse_its):
     assert conv and its <= bound, (label, its)
 
 
+@pytest.mark.parametrize("kw", [dict(smooth_order=(1, -1)), dict(smooth_order=(1, -1), c_inverse_sparsity_order=0)], ids=["fc", "fc_c_sparsity0"])
+def test_pin_advection_8x8_fc_smoothing(built_libs, kw):
+    """tests/Makefile:299-303: `adv_diff_fd -da_grid_x 8 -da_grid_y 8 -pc_type air -ksp_max_it 3 -pc_air_smooth_type fc
+    [-pc_air_c_inverse_sparsity_order 0]`: one F and one C smooth per level (c_smooths, src/FC_Smooth.F90:572-640)."""
+    from hiergen import AirOptions
+    A = hiergen.adv_diff_fd(8, 8)
+    n = A.shape[0]
+    O = _oracle(hiergen.build_hierarchy(A, AirOptions(**kw)))
+    _, its, conv = gmres(A, np.zeros(n), np.ones(n), O.apply, rtol=1e-5, side="left")
+    assert conv and its <= 3, its
+
+
 def test_pin_e05r0100_power(built_libs):
     """tests/Makefile:157: `ex6 -f data/e05r0100_petsc -b_in_f 0 -pc_air_a_drop 1e-3 -pc_air_inverse_type power -ksp_max_it 26` on the
     reference's data fixture (b = 0, random initial guess, GMRES rtol 1e-5): a hard non-symmetric problem where AIRG needs ~23 iterations."""
